@@ -1,0 +1,570 @@
+// ofdm_b200.cu -- context, launch geometry and the extern "C" boundary of libofdm_b200.so.
+// Every entry point of include/ofdm_b200.h is defined here (writers live in host/ofdm_io.c).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "ofdm_kernels.cuh"
+
+using namespace ofdm;
+
+struct ofdm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    uint64_t launches = 0;
+    char err[256] = {0};
+    float lts_freq[128];
+    float lts_time[320];
+    // cached scratch (grown on demand, released with the context)
+    void *scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+const signed char kLk[53] = {1, 1, -1, -1, 1, 1, -1, 1, -1, 1, 1, 1, 1, 1, 1, -1, -1, 1, 1, -1, 1, -1, 1, 1, 1, 1, 0,
+                             1, -1, -1, 1, 1, -1, 1, -1, 1, -1, -1, -1, -1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, 1, 1};
+
+int fail(ofdm_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (ctx) {
+        if (e != cudaSuccess) snprintf(ctx->err, sizeof ctx->err, "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(ctx->err, sizeof ctx->err, "%s", what);
+    }
+    return status;
+}
+
+#define OFDM_CUDA(ctx, call)                                                   \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) return fail((ctx), OFDM_ERR_CUDA, #call, e_);   \
+    } while (0)
+
+#define OFDM_REQUIRE(ctx, cond)                                                          \
+    do {                                                                                 \
+        if (!(cond)) return fail((ctx), OFDM_ERR_INVALID, "invalid argument: " #cond);   \
+    } while (0)
+
+int check_launch(ofdm_ctx *ctx, const char *name)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, OFDM_ERR_CUDA, name, e);
+    ctx->launches += 1;
+    return OFDM_OK;
+}
+
+int bind(ofdm_ctx *ctx)
+{
+    if (!ctx) return OFDM_ERR_INVALID;
+    OFDM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return OFDM_OK;
+}
+
+// persistent launch geometry: resident blocks per SM (from the occupancy calculator) x SM count,
+// capped by the amount of work
+template <typename K>
+int grid_for(ofdm_ctx *ctx, K kernel, size_t dyn_smem, long work_items_per_block_iter, long work)
+{
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    long full = (long)per_sm * ctx->sm_count;
+    long need = (work + work_items_per_block_iter - 1) / work_items_per_block_iter;
+    long g = need < full ? need : full;
+    return (int)(g < 1 ? 1 : g);
+}
+
+int ensure_scratch(ofdm_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) { cudaFree(ctx->scratch[slot]); ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; }
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], bytes);
+        if (e != cudaSuccess) return fail(ctx, OFDM_ERR_NOMEM, "cudaMalloc(scratch)", e);
+        ctx->scratch_bytes[slot] = bytes;
+    }
+    *out = ctx->scratch[slot];
+    return OFDM_OK;
+}
+
+float snr_linear(float snr_db)
+{
+    // float snr_linear = pow(10, snr / 10);   OFDM.c:645  (float / int -> float, pow in double, rounded to float)
+    return (float)pow(10.0, (double)(snr_db / 10));
+}
+
+int upload_tables(ofdm_ctx *ctx, const float *lts_time /* nullable */)
+{
+    Tables t;
+    memset(&t, 0, sizeof t);
+    for (int k = 0; k < 32; ++k) t.tw64[k] = make_double2(kTw64[k][0], kTw64[k][1]);
+    for (int k = 0; k < 64; ++k) {
+        double a = 2.0 * 3.14159265358979323846 * k / 64.0;
+        t.tw64f[k] = make_float2((float)cos(a), (float)(-sin(a)));
+    }
+    // centred index c -> data index (runs of OFDM.c:528-547): c = 6..10, 12..24, 26..31, 33..38, 40..52, 54..58
+    signed char by_c[64];
+    for (int c = 0; c < 64; ++c) by_c[c] = -1;
+    const int lo[6] = {6, 12, 26, 33, 40, 54}, hi[6] = {10, 24, 31, 38, 52, 58};
+    int d = 0;
+    for (int r = 0; r < 6; ++r) for (int c = lo[r]; c <= hi[r]; ++c) by_c[c] = (signed char)d++;
+    by_c[11] = -2; by_c[25] = -2; by_c[39] = -2; by_c[53] = -3;           // pilots {1,1,1,-1} OFDM.c:523
+    for (int p = 0; p < 64; ++p) {
+        int c = (p + 32) & 63;
+        t.bin_data[p] = by_c[c];
+        t.bin_lts[p] = (c >= 6 && c <= 58) ? kLk[c - 6] : 0;
+    }
+    if (lts_time) memcpy(t.lts_time, lts_time, sizeof t.lts_time);
+    OFDM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, ctx->stream));
+    OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OFDM_OK;
+}
+
+template <bool EXACT, bool INV>
+int launch_fft(ofdm_ctx *ctx, const float *in, float *out, long n)
+{
+    auto k = k_fft64<EXACT, INV>;
+    int grid = grid_for(ctx, k, 0, kWarpsPerBlock * 4, n);
+    k<<<grid, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), n);
+    return check_launch(ctx, "k_fft64");
+}
+
+template <bool EXACT, int NOISE>
+int launch_rx(ofdm_ctx *ctx, const RxParams &p)
+{
+    auto k = k_rx_frames<EXACT, NOISE>;
+    int grid = grid_for(ctx, k, 0, kWarpsPerBlock, p.n_frames);
+    k<<<grid, kThreads, 0, ctx->stream>>>(p);
+    return check_launch(ctx, "k_rx_frames");
+}
+
+int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
+{
+    if (mode == OFDM_MODE_EXACT) {
+        if (noise == kNoiseNone) return launch_rx<true, kNoiseNone>(ctx, p);
+        if (noise == kNoiseInject) return launch_rx<true, kNoiseInject>(ctx, p);
+        return launch_rx<true, kNoisePhilox>(ctx, p);
+    }
+    if (noise == kNoiseNone) return launch_rx<false, kNoiseNone>(ctx, p);
+    if (noise == kNoiseInject) return launch_rx<false, kNoiseInject>(ctx, p);
+    return launch_rx<false, kNoisePhilox>(ctx, p);
+}
+
+int frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames, int len, int mode)
+{
+    if (mode == OFDM_MODE_EXACT) {
+        size_t smem = (size_t)kWarpsPerBlock * len * sizeof(double);
+        if (smem > 48 * 1024)
+            OFDM_CUDA(ctx, cudaFuncSetAttribute(k_frame_power_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = grid_for(ctx, k_frame_power_exact, smem, kWarpsPerBlock, n_frames);
+        k_frame_power_exact<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), power, n_frames, len);
+        return check_launch(ctx, "k_frame_power_exact");
+    }
+    int grid = grid_for(ctx, k_frame_power_fast, 0, kWarpsPerBlock, n_frames);
+    k_frame_power_fast<<<grid, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), power, n_frames, len);
+    return check_launch(ctx, "k_frame_power_fast");
+}
+
+bool mode_ok(int mode) { return mode == OFDM_MODE_EXACT || mode == OFDM_MODE_FAST; }
+bool nsym_ok(int n_sym) { return n_sym >= 1 && n_sym <= OFDM_MAX_SYM; }
+
+int blocks_1d(long n) { return (int)((n + 255) / 256); }
+
+}  // namespace
+
+extern "C" {
+
+int ofdm_version(void) { return OFDM_B200_VERSION; }
+
+const char *ofdm_strerror(int status)
+{
+    switch (status) {
+    case OFDM_OK: return "ok";
+    case OFDM_ERR_INVALID: return "invalid argument";
+    case OFDM_ERR_CUDA: return "CUDA runtime error";
+    case OFDM_ERR_NOMEM: return "out of memory";
+    case OFDM_ERR_IO: return "file I/O error";
+    case OFDM_ERR_NODEVICE: return "no CUDA device (this library has no CPU fallback)";
+    default: return "unknown status";
+    }
+}
+
+int ofdm_ctx_create(ofdm_ctx **out, int device)
+{
+    if (!out) return OFDM_ERR_INVALID;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) { cudaGetLastError(); return OFDM_ERR_NODEVICE; }
+    if (device < 0 || device >= n_dev) return OFDM_ERR_INVALID;
+    ofdm_ctx *ctx = new (std::nothrow) ofdm_ctx();
+    if (!ctx) return OFDM_ERR_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return OFDM_ERR_CUDA; }
+    ctx->owns_stream = true;
+
+    // LTS: Preamble_Generator(type 1) OFDM.c:368-399 -- frequency grid from L_k at c = 6..58, time slot through
+    // this library's own exact ifft kernel, then [samples 32..63][0..63][0..63]
+    int st = upload_tables(ctx, nullptr);
+    float *d_buf = nullptr;
+    if (st == OFDM_OK && cudaMalloc(&d_buf, 2 * 128 * sizeof(float)) != cudaSuccess) st = OFDM_ERR_NOMEM;
+    if (st == OFDM_OK) {
+        memset(ctx->lts_freq, 0, sizeof ctx->lts_freq);
+        for (int i = 0; i < 53; ++i) ctx->lts_freq[2 * (6 + i)] = (float)kLk[i];
+        float t64[128];
+        if (cudaMemcpyAsync(d_buf, ctx->lts_freq, sizeof ctx->lts_freq, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+        if (st == OFDM_OK) st = launch_fft<true, true>(ctx, d_buf, d_buf + 128, 1);
+        if (st == OFDM_OK && cudaMemcpyAsync(t64, d_buf + 128, sizeof t64, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+        if (st == OFDM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+        if (st == OFDM_OK) {
+            memcpy(ctx->lts_time, t64 + 64, 32 * 2 * sizeof(float));                 // :396
+            memcpy(ctx->lts_time + 64, t64, 64 * 2 * sizeof(float));                 // :397 (first copy)
+            memcpy(ctx->lts_time + 64 + 128, t64, 64 * 2 * sizeof(float));           // :397 (second copy)
+            st = upload_tables(ctx, ctx->lts_time);
+        }
+    }
+    if (d_buf) cudaFree(d_buf);
+    if (st != OFDM_OK) { ofdm_ctx_destroy(ctx); return st; }
+    *out = ctx;
+    return OFDM_OK;
+}
+
+int ofdm_ctx_destroy(ofdm_ctx *ctx)
+{
+    if (!ctx) return OFDM_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 6; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return OFDM_OK;
+}
+
+const char *ofdm_last_error(const ofdm_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int ofdm_ctx_set_stream(ofdm_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return OFDM_ERR_INVALID;
+    if (ctx->owns_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->owns_stream = false;
+    return OFDM_OK;
+}
+void *ofdm_ctx_stream(const ofdm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int ofdm_ctx_sync(ofdm_ctx *ctx)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OFDM_OK;
+}
+int ofdm_ctx_sm_count(const ofdm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t ofdm_ctx_launch_count(const ofdm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ofdm_dev_alloc(ofdm_ctx *ctx, void **ptr, size_t bytes)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, ptr != nullptr);
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { *ptr = nullptr; return fail(ctx, OFDM_ERR_NOMEM, "cudaMalloc", e); }
+    return OFDM_OK;
+}
+int ofdm_dev_free(ofdm_ctx *ctx, void *ptr)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_CUDA(ctx, cudaFree(ptr));
+    return OFDM_OK;
+}
+int ofdm_host_alloc(ofdm_ctx *ctx, void **ptr, size_t bytes)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, ptr != nullptr);
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { *ptr = nullptr; return fail(ctx, OFDM_ERR_NOMEM, "cudaMallocHost", e); }
+    return OFDM_OK;
+}
+int ofdm_host_free(ofdm_ctx *ctx, void *ptr)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_CUDA(ctx, cudaFreeHost(ptr));
+    return OFDM_OK;
+}
+int ofdm_memcpy_h2d(ofdm_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (int st = bind(ctx)) return st;
+    if (bytes == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, dst != nullptr && src != nullptr);
+    OFDM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return OFDM_OK;
+}
+int ofdm_memcpy_d2h(ofdm_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (int st = bind(ctx)) return st;
+    if (bytes == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, dst != nullptr && src != nullptr);
+    OFDM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return OFDM_OK;
+}
+int ofdm_memset_dev(ofdm_ctx *ctx, void *dst, int value, size_t bytes)
+{
+    if (int st = bind(ctx)) return st;
+    if (bytes == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, dst != nullptr);
+    OFDM_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return OFDM_OK;
+}
+
+// ------------------------------------------------------------------ stage-level
+int ofdm_pack_bits(ofdm_ctx *ctx, const uint8_t *bits, uint32_t *packed, long n_symbols)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_symbols >= 0);
+    if (n_symbols == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, bits != nullptr && packed != nullptr);
+    long n_words = n_symbols * 3;
+    k_pack_bits<<<blocks_1d(n_words), 256, 0, ctx->stream>>>(bits, packed, n_words);
+    return check_launch(ctx, "k_pack_bits");
+}
+int ofdm_unpack_bits(ofdm_ctx *ctx, const uint32_t *packed, uint8_t *bits, long n_symbols)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_symbols >= 0);
+    if (n_symbols == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, bits != nullptr && packed != nullptr);
+    long n_bits = n_symbols * 96;
+    k_unpack_bits<<<blocks_1d(n_bits), 256, 0, ctx->stream>>>(packed, bits, n_bits);
+    return check_launch(ctx, "k_unpack_bits");
+}
+int ofdm_qpsk_modulate(ofdm_ctx *ctx, const uint32_t *bits, float *mod, long n_symbols)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_symbols >= 0);
+    if (n_symbols == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, bits != nullptr && mod != nullptr);
+    long n = n_symbols * 48;
+    k_qpsk_mod<<<blocks_1d(n), 256, 0, ctx->stream>>>(bits, reinterpret_cast<float2 *>(mod), n);
+    return check_launch(ctx, "k_qpsk_mod");
+}
+int ofdm_map_subcarriers(ofdm_ctx *ctx, const float *mod, float *grid, long n_symbols)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_symbols >= 0);
+    if (n_symbols == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, mod != nullptr && grid != nullptr);
+    long n = n_symbols * 64;
+    k_map_subcarriers<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(mod), reinterpret_cast<float2 *>(grid), n);
+    return check_launch(ctx, "k_map_subcarriers");
+}
+int ofdm_ifft64(ofdm_ctx *ctx, const float *in, float *out, long n, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0 && mode_ok(mode));
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && in != out);
+    return mode == OFDM_MODE_EXACT ? launch_fft<true, true>(ctx, in, out, n) : launch_fft<false, true>(ctx, in, out, n);
+}
+int ofdm_fft64(ofdm_ctx *ctx, const float *in, float *out, long n, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0 && mode_ok(mode));
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && in != out);
+    return mode == OFDM_MODE_EXACT ? launch_fft<true, false>(ctx, in, out, n) : launch_fft<false, false>(ctx, in, out, n);
+}
+int ofdm_add_cp(ofdm_ctx *ctx, const float *sym, float *out, long n)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0);
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, sym != nullptr && out != nullptr);
+    k_add_cp<<<blocks_1d(n * 80), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(sym), reinterpret_cast<float2 *>(out), n * 80);
+    return check_launch(ctx, "k_add_cp");
+}
+int ofdm_lts(ofdm_ctx *ctx, float *lts_freq_host, float *lts_time_host)
+{
+    if (!ctx) return OFDM_ERR_INVALID;
+    if (lts_freq_host) memcpy(lts_freq_host, ctx->lts_freq, sizeof ctx->lts_freq);
+    if (lts_time_host) memcpy(lts_time_host, ctx->lts_time, sizeof ctx->lts_time);
+    return OFDM_OK;
+}
+
+int ofdm_frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames, int frame_len, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= OFDM_FRAME_LEN(OFDM_MAX_SYM) && mode_ok(mode));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, frames != nullptr && power != nullptr);
+    return frame_power(ctx, frames, power, n_frames, frame_len, mode);
+}
+
+int ofdm_tx_frames(ofdm_ctx *ctx, const uint32_t *bits, float *frames, float *power, long n_frames, int n_sym, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, bits != nullptr && frames != nullptr);
+    int st;
+    if (mode == OFDM_MODE_EXACT) {
+        int grid = grid_for(ctx, k_tx_frames<true>, 0, kWarpsPerBlock * 4, n_frames * n_sym);
+        k_tx_frames<true><<<grid, kThreads, 0, ctx->stream>>>(bits, reinterpret_cast<float2 *>(frames), n_frames, n_sym);
+        st = check_launch(ctx, "k_tx_frames<exact>");
+    } else {
+        int grid = grid_for(ctx, k_tx_frames<false>, 0, kWarpsPerBlock * 4, n_frames * n_sym);
+        k_tx_frames<false><<<grid, kThreads, 0, ctx->stream>>>(bits, reinterpret_cast<float2 *>(frames), n_frames, n_sym);
+        st = check_launch(ctx, "k_tx_frames<fast>");
+    }
+    if (st != OFDM_OK || power == nullptr) return st;
+    return frame_power(ctx, frames, power, n_frames, OFDM_FRAME_LEN(n_sym), mode);
+}
+
+static int resolve_power(ofdm_ctx *ctx, const float *tx, const float *power, long n_frames, int len, int mode, const float **out)
+{
+    if (power) { *out = power; return OFDM_OK; }
+    void *buf = nullptr;
+    if (int st = ensure_scratch(ctx, 0, (size_t)n_frames * sizeof(float), &buf)) return st;
+    if (int st = frame_power(ctx, tx, (float *)buf, n_frames, len, mode)) return st;
+    *out = (const float *)buf;
+    return OFDM_OK;
+}
+
+static int awgn_common(ofdm_ctx *ctx, int noise, const float *tx, const float *g, const float *power, float snr_db,
+                       uint32_t seed, uint32_t stream, uint64_t frame0, float *ota, long n_frames, int n_sym, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, tx != nullptr && ota != nullptr && (noise != kNoiseInject || g != nullptr));
+    const int len = OFDM_FRAME_LEN(n_sym);
+    const float *pw = nullptr;
+    if (int st = resolve_power(ctx, tx, power, n_frames, len, mode, &pw)) return st;
+    const float2 *x = reinterpret_cast<const float2 *>(tx);
+    float2 *y = reinterpret_cast<float2 *>(ota);
+    const float sl = snr_linear(snr_db);
+#define LAUNCH_AWGN(E, N)                                                                                         \
+    do {                                                                                                          \
+        int grid = grid_for(ctx, k_awgn<E, N>, 0, kWarpsPerBlock, n_frames);                                      \
+        k_awgn<E, N><<<grid, kThreads, 0, ctx->stream>>>(x, g, pw, sl, seed, stream, frame0, y, n_frames, len);   \
+    } while (0)
+    if (mode == OFDM_MODE_EXACT) { if (noise == kNoiseInject) LAUNCH_AWGN(true, kNoiseInject); else LAUNCH_AWGN(true, kNoisePhilox); }
+    else { if (noise == kNoiseInject) LAUNCH_AWGN(false, kNoiseInject); else LAUNCH_AWGN(false, kNoisePhilox); }
+#undef LAUNCH_AWGN
+    return check_launch(ctx, "k_awgn");
+}
+
+int ofdm_awgn_inject(ofdm_ctx *ctx, const float *tx, const float *g, const float *power, float snr_db, float *ota,
+                     long n_frames, int n_sym, int mode)
+{
+    return awgn_common(ctx, kNoiseInject, tx, g, power, snr_db, 0, 0, 0, ota, n_frames, n_sym, mode);
+}
+int ofdm_awgn_philox(ofdm_ctx *ctx, const float *tx, const float *power, float snr_db, uint32_t seed, uint32_t stream,
+                     uint64_t frame0, float *ota, long n_frames, int n_sym, int mode)
+{
+    return awgn_common(ctx, kNoisePhilox, tx, nullptr, power, snr_db, seed, stream, frame0, ota, n_frames, n_sym, mode);
+}
+
+static int rx_common(ofdm_ctx *ctx, int noise, const float *in, const float *g, const float *power, const uint32_t *tx_bits,
+                     float snr_db, uint32_t seed, uint32_t stream, uint64_t frame0, long n_frames, int n_sym, int mode,
+                     ofdm_counters *counters, const ofdm_rx_dump *dump)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, in != nullptr && tx_bits != nullptr && (noise != kNoiseInject || g != nullptr));
+    RxParams p;
+    memset(&p, 0, sizeof p);
+    p.in = reinterpret_cast<const float2 *>(in);
+    p.g = g;
+    p.tx_bits = tx_bits;
+    p.n_frames = n_frames;
+    p.n_sym = n_sym;
+    p.snr_lin = snr_linear(snr_db);
+    p.seed = seed; p.stream = stream; p.frame0 = frame0;
+    p.counters = counters;
+    if (dump) p.dump = *dump;
+    if (noise != kNoiseNone) {
+        if (int st = resolve_power(ctx, in, power, n_frames, OFDM_FRAME_LEN(n_sym), mode, &p.power)) return st;
+    }
+    return launch_rx_any(ctx, mode, noise, p);
+}
+
+int ofdm_rx_frames(ofdm_ctx *ctx, const float *ota, const uint32_t *tx_bits, long n_frames, int n_sym, int mode,
+                   ofdm_counters *counters, const ofdm_rx_dump *dump)
+{
+    return rx_common(ctx, kNoiseNone, ota, nullptr, nullptr, tx_bits, 0.f, 0, 0, 0, n_frames, n_sym, mode, counters, dump);
+}
+int ofdm_awgn_rx_inject(ofdm_ctx *ctx, const float *tx, const float *g, const float *power, const uint32_t *tx_bits,
+                        float snr_db, long n_frames, int n_sym, int mode, ofdm_counters *counters, const ofdm_rx_dump *dump)
+{
+    return rx_common(ctx, kNoiseInject, tx, g, power, tx_bits, snr_db, 0, 0, 0, n_frames, n_sym, mode, counters, dump);
+}
+int ofdm_awgn_rx_philox(ofdm_ctx *ctx, const float *tx, const float *power, const uint32_t *tx_bits, float snr_db,
+                        uint32_t seed, uint32_t stream, uint64_t frame0, long n_frames, int n_sym, int mode,
+                        ofdm_counters *counters, const ofdm_rx_dump *dump)
+{
+    return rx_common(ctx, kNoisePhilox, tx, nullptr, power, tx_bits, snr_db, seed, stream, frame0, n_frames, n_sym, mode,
+                     counters, dump);
+}
+
+// ------------------------------------------------------------------ sweep drivers
+int ofdm_sweep_inject_dev(ofdm_ctx *ctx, const uint32_t *bits, const float *g, long n_frames, int n_sym,
+                          const float *snr_db, int n_snr, int mode, ofdm_counters *out_host)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0);
+    OFDM_REQUIRE(ctx, n_snr == 0 || (snr_db != nullptr && out_host != nullptr));
+    memset(out_host, 0, sizeof(ofdm_counters) * (size_t)n_snr);
+    if (n_frames == 0 || n_snr == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, bits != nullptr && g != nullptr);
+    const int len = OFDM_FRAME_LEN(n_sym);
+    void *frames = nullptr, *power = nullptr, *cnt = nullptr;
+    if (int st = ensure_scratch(ctx, 1, (size_t)n_frames * len * 2 * sizeof(float), &frames)) return st;
+    if (int st = ensure_scratch(ctx, 2, (size_t)n_frames * sizeof(float), &power)) return st;
+    if (int st = ensure_scratch(ctx, 3, sizeof(ofdm_counters) * (size_t)n_snr, &cnt)) return st;
+    OFDM_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(ofdm_counters) * (size_t)n_snr, ctx->stream));
+    // Transmitter() runs once (OFDM.c:1191); the SNR loop (OFDM.c:1202-1222) reruns channel + receiver
+    if (int st = ofdm_tx_frames(ctx, bits, (float *)frames, (float *)power, n_frames, n_sym, mode)) return st;
+    for (int i = 0; i < n_snr; ++i) {
+        if (int st = ofdm_awgn_rx_inject(ctx, (const float *)frames, g, (const float *)power, bits, snr_db[i], n_frames, n_sym,
+                                         mode, (ofdm_counters *)cnt + i, nullptr))
+            return st;
+    }
+    OFDM_CUDA(ctx, cudaMemcpyAsync(out_host, cnt, sizeof(ofdm_counters) * (size_t)n_snr, cudaMemcpyDeviceToHost, ctx->stream));
+    OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OFDM_OK;
+}
+
+int ofdm_sweep_inject_host(ofdm_ctx *ctx, const uint32_t *bits_host, const float *g_host, long n_frames, int n_sym,
+                           const float *snr_db, int n_snr, int mode, ofdm_counters *out_host)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0);
+    if (n_frames == 0 || n_snr == 0) return ofdm_sweep_inject_dev(ctx, nullptr, nullptr, n_frames, n_sym, snr_db, n_snr, mode, out_host);
+    OFDM_REQUIRE(ctx, bits_host != nullptr && g_host != nullptr);
+    const int len = OFDM_FRAME_LEN(n_sym);
+    void *bits = nullptr, *g = nullptr;
+    const size_t bits_bytes = (size_t)n_frames * n_sym * 3 * sizeof(uint32_t), g_bytes = (size_t)n_frames * len * sizeof(float);
+    if (int st = ensure_scratch(ctx, 4, bits_bytes, &bits)) return st;
+    if (int st = ensure_scratch(ctx, 5, g_bytes, &g)) return st;
+    OFDM_CUDA(ctx, cudaMemcpyAsync(bits, bits_host, bits_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    OFDM_CUDA(ctx, cudaMemcpyAsync(g, g_host, g_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ofdm_sweep_inject_dev(ctx, (const uint32_t *)bits, (const float *)g, n_frames, n_sym, snr_db, n_snr, mode, out_host);
+}
+
+int ofdm_counters_finalize(const ofdm_counters *c, float res[3])
+{
+    if (!c || !res) return OFDM_ERR_INVALID;
+    // evm = sqrt(err/N) / sqrt(ref/N), dB = 20*log10   OFDM.c:1124-1126; after the slicer every rail error
+    // contributes (2/sqrt(2))^2 to the error energy, OFDM.c:1138-1139
+    const double q = (double)kQpsk;
+    double evm = sqrt(c->sum_err2 / c->sum_ref2);
+    double evm_agc = sqrt((double)c->rail_errors * (2.0 * q) * (2.0 * q) / c->sum_ref2);
+    res[0] = (float)(20.0 * log10(evm));
+    res[1] = (float)(20.0 * log10(evm_agc));
+    res[2] = c->bits ? (float)((double)c->bit_errors / (double)c->bits) : 0.f;   // OFDM.c:1161
+    return OFDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,440 @@
+// ofdm_kernels.cuh -- the __global__ kernels of the stage chain (see ofdm_device.cuh for the
+// work decomposition).  Included once, by ofdm_b200.cu.
+#pragma once
+#include "ofdm_device.cuh"
+#include "../../include/ofdm_b200.h"
+
+namespace ofdm {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+enum { kNoiseNone = 0, kNoiseInject = 1, kNoisePhilox = 2 };
+
+// ------------------------------------------------------------------ layout helpers
+// one byte per bit -> 3 packed words per symbol (OFDM.c stores bits as float complex; the
+// byte form is what a host-side caller naturally has)
+__global__ void k_pack_bits(const uint8_t *__restrict__ bits, uint32_t *__restrict__ packed, long n_words)
+{
+    long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const uint8_t *b = bits + w * 32;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v |= (uint32_t)(b[j] & 1u) << j;
+    packed[w] = v;
+}
+__global__ void k_unpack_bits(const uint32_t *__restrict__ packed, uint8_t *__restrict__ bits, long n_bits)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bits) return;
+    bits[i] = (uint8_t)((packed[i >> 5] >> (i & 31)) & 1u);
+}
+
+// QPSK_Modulator OFDM.c:415-433; one thread per constellation point
+__global__ void k_qpsk_mod(const uint32_t *__restrict__ bits, float2 *__restrict__ mod, long n_points)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    long sym = i / 48; int d = (int)(i - sym * 48);
+    const uint32_t *w = bits + sym * 3;
+    mod[i] = qpsk_point(bit_pair(w[0], w[1], w[2], d));
+}
+
+// frame-build block OFDM.c:523-548; one thread per grid bin (centred index c)
+__global__ void k_map_subcarriers(const float2 *__restrict__ mod, float2 *__restrict__ grid, long n_bins)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bins) return;
+    long sym = i >> 6; int c = (int)(i & 63);
+    int d = c_tab.bin_data[(c + 32) & 63];
+    float2 v = make_float2(0.f, 0.f);
+    if (d >= 0) v = mod[sym * 48 + d];
+    else if (d == -2) v.x = 1.f;
+    else if (d == -3) v.x = -1.f;
+    grid[i] = v;
+}
+
+// CP add OFDM.c:559-565
+__global__ void k_add_cp(const float2 *__restrict__ sym, float2 *__restrict__ out, long n_out)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    long s = i / 80; int k = (int)(i - s * 80);
+    out[i] = sym[s * 64 + (k < 16 ? 48 + k : k - 16)];
+}
+
+// ------------------------------------------------------------------ stand-alone transforms
+// fft OFDM.c:314-318 (INVERSE = false) and ifft OFDM.c:320-339 (INVERSE = true) on [n][64]
+// centred buffers, one 8-lane group per transform.
+template <bool EXACT, bool INVERSE>
+__global__ void __launch_bounds__(kThreads) k_fft64(const float2 *__restrict__ in, float2 *__restrict__ out, long n)
+{
+    __shared__ float2 s_tile[kWarpsPerBlock][kWarpTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    float2 *tile = s_tile[warp] + grp * kGroupPitch;
+    Tw<EXACT> tw; tw.load(u);
+    const long n_groups = (long)gridDim.x * kWarpsPerBlock * 4;
+    const long iters = (n + n_groups - 1) / n_groups;
+    for (long it = 0; it < iters; ++it) {
+        long t = it * n_groups + ((long)blockIdx.x * kWarpsPerBlock + warp) * 4 + grp;
+        bool active = t < n;
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int nn = 8 * slot_m<EXACT>(i) + u;                 // natural input index
+            float2 x = make_float2(0.f, 0.f);
+            if (active) {
+                if (INVERSE) { x = in[t * 64 + ((nn + 32) & 63)]; x.y = -x.y; }   // ifft_shift :208 + conj :328
+                else x = in[t * 64 + nn];
+            }
+            v[i] = x;
+        }
+        fft64<EXACT>(v, tw, tile, u);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int c = (u + 8 * j + 32) & 63;                  // fft_shift :227
+                float2 y = v[j];
+                if (INVERSE) { y.x = y.x * 0.015625f; y.y = -y.y * 0.015625f; }   // conj, /sz :334 (exact scaling)
+                out[t * 64 + c] = y;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ transmitter
+// Transmitter OFDM.c:500-581 (QPSK map, subcarrier/pilot map, ifft, CP, LTS || data concat) fused:
+// bits in, frame IQ out, nothing else touches HBM.  One 8-lane group per OFDM symbol.
+template <bool EXACT>
+__global__ void __launch_bounds__(kThreads) k_tx_frames(const uint32_t *__restrict__ bits, float2 *__restrict__ frames,
+                                                        long n_frames, int n_sym)
+{
+    __shared__ float2 s_tile[kWarpsPerBlock][kWarpTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    float2 *tile = s_tile[warp] + grp * kGroupPitch;
+    Tw<EXACT> tw; tw.load(u);
+    int dmap[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmap[i] = c_tab.bin_data[8 * slot_m<EXACT>(i) + u];   // input index n <-> centred (n+32)%64
+    const int len = 160 + 80 * n_sym;
+    const long n_symbols = n_frames * n_sym;
+    const long n_groups = (long)gridDim.x * kWarpsPerBlock * 4;
+    const long iters = (n_symbols + n_groups - 1) / n_groups;
+    for (long it = 0; it < iters; ++it) {
+        long t = it * n_groups + ((long)blockIdx.x * kWarpsPerBlock + warp) * 4 + grp;
+        bool active = t < n_symbols;
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (active) { const uint32_t *w = bits + t * 3; w0 = w[0]; w1 = w[1]; w2 = w[2]; }
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // grid value at centred index (n+32)%64 (ifft_shift :208), conjugated (:328)
+            int d = dmap[i];
+            float2 x = make_float2(0.f, -0.f);
+            if (d >= 0) { x = qpsk_point(bit_pair(w0, w1, w2, d)); x.y = -x.y; }
+            else if (d == -2) x.x = 1.f;
+            else if (d == -3) x.x = -1.f;
+            v[i] = x;
+        }
+        fft64<EXACT>(v, tw, tile, u);
+        if (active) {
+            long f = t / n_sym; int s = (int)(t - f * n_sym);
+            float2 *fr = frames + f * len;
+            float2 *dst = fr + 160 + 80 * s;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int np = u + 8 * ((j + 4) & 7);                 // fft_shift inside ifft's fft() -> 32-sample rotation (Q4)
+                float2 y = make_float2(v[j].x * 0.015625f, -v[j].y * 0.015625f);
+                dst[16 + np] = y;                               // body :564
+                if (np >= 48) dst[np - 48] = y;                 // CP   :563
+            }
+            if (s == 0) {                                       // LTS slot :573 (constant, built at context creation)
+#pragma unroll
+                for (int k = 0; k < 20; ++k) fr[u + 8 * k] = c_tab.lts_time[u + 8 * k];
+            }
+        }
+    }
+}
+
+// signal power of Transmission_Over_Air OFDM.c:637-643.  EXACT: double terms cabs*cabs (glibc hypot),
+// accumulated sequentially into a float, one warp per frame (terms in parallel, chain on lane 0).
+__global__ void __launch_bounds__(kThreads) k_frame_power_exact(const float2 *__restrict__ frames, float *__restrict__ power,
+                                                                long n_frames, int len)
+{
+    extern __shared__ double s_terms[];                         // [warps][len]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *terms = s_terms + (size_t)warp * len;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float2 *x = frames + f * len;
+        for (int i = lane; i < len; i += 32) {
+            float2 s = x[i];
+            double h = hypot_glibc((double)s.x, (double)s.y);
+            terms[i] = __dmul_rn(h, h);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float p = 0.f;
+            for (int i = 0; i < len; ++i) p = __double2float_rn(__dadd_rn((double)p, terms[i]));
+            power[f] = __fdiv_rn(p, (float)len);
+        }
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_frame_power_fast(const float2 *__restrict__ frames, float *__restrict__ power,
+                                                               long n_frames, int len)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float2 *x = frames + f * len;
+        float acc = 0.f;
+        for (int i = lane; i < len; i += 32) { float2 s = x[i]; acc = fmaf(s.x, s.x, fmaf(s.y, s.y, acc)); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) power[f] = acc / (float)len;
+    }
+}
+
+// ------------------------------------------------------------------ channel (stand-alone)
+// Transmission_Over_Air OFDM.c:645-653 with per-frame power: y.re = x.re + (float)(sqrt((double)np)*g),
+// y.im = x.im.  One warp per frame.
+__device__ __forceinline__ void noise_slot(int n, int &blk, int &j)
+{
+    if (n < 32) { blk = n >> 2; j = n & 3; return; }
+    int base, l;
+    if (n < 160) { l = (n - 32) & 63; base = n < 96 ? 8 : 24; }
+    else {
+        int s = (n - 160) / 80; l = (n - 160) - 80 * s;
+        if (l < 16) { blk = 40 + 20 * s + (l >> 2); j = l & 3; return; }
+        l -= 16; base = 44 + 20 * s;
+    }
+    blk = base + (l & 7) + 8 * (l >> 5);
+    j = (l >> 3) & 3;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float add_noise(float xr, float g, double sigma_d, float sigma_f)
+{
+    if constexpr (EXACT) return __fadd_rn(xr, __double2float_rn(__dmul_rn(sigma_d, (double)g)));
+    else return fmaf(sigma_f, g, xr);
+}
+
+template <bool EXACT, int NOISE>
+__global__ void __launch_bounds__(kThreads) k_awgn(const float2 *__restrict__ tx, const float *__restrict__ g,
+                                                   const float *__restrict__ power, float snr_lin, uint32_t seed,
+                                                   uint32_t stream, uint64_t frame0, float2 *__restrict__ ota,
+                                                   long n_frames, int len)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        float np = __fdiv_rn(power[f], snr_lin);                // :647
+        double sigma_d = __dsqrt_rn((double)np);                // sqrt(noise_power) in double, :651
+        float sigma_f = (float)sigma_d;
+        const float2 *x = tx + f * len;
+        float2 *y = ota + f * len;
+        for (int n = lane; n < len; n += 32) {
+            float2 s = x[n];
+            float gn;
+            if (NOISE == kNoiseInject) gn = g[f * len + n];
+            else {
+                int blk, j; noise_slot(n, blk, j);
+                float z[4];
+                philox_normals4(seed, stream, frame0 + (uint64_t)f, (uint32_t)blk, kDomainNoise, z);
+                gn = j == 0 ? z[0] : (j == 1 ? z[1] : (j == 2 ? z[2] : z[3]));
+            }
+            s.x = add_noise<EXACT>(s.x, gn, sigma_d, sigma_f);
+            y[n] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ receiver (optionally fused with the channel)
+struct RxParams {
+    const float2 *in;           // OTA frames (NOISE == none) or TX frames (noise added in registers)
+    const float *g;             // injected normals
+    const float *power;         // per-frame mean power
+    const uint32_t *tx_bits;
+    long n_frames;
+    int n_sym;
+    float snr_lin;
+    uint32_t seed, stream;
+    uint64_t frame0;
+    ofdm_counters *counters;
+    ofdm_rx_dump dump;
+};
+
+// libgcc __divsc3 as gcc 13 builds it: quotient formula in double, one rounding to float, plus its
+// zero-denominator recovery.  OFDM.c:1050
+__device__ __forceinline__ float2 div_exact(float2 n, float2 h)
+{
+    double a = n.x, b = n.y, c = h.x, d = h.y;
+    double den = __dadd_rn(__dmul_rn(c, c), __dmul_rn(d, d));
+    double x = __ddiv_rn(__dadd_rn(__dmul_rn(a, c), __dmul_rn(b, d)), den);
+    double y = __ddiv_rn(__dsub_rn(__dmul_rn(b, c), __dmul_rn(a, d)), den);
+    if (isnan(x) && isnan(y) && den == 0.0 && (!isnan(a) || !isnan(b))) {
+        double inf = copysign((double)INFINITY, c);
+        x = __dmul_rn(inf, a); y = __dmul_rn(inf, b);
+    }
+    return make_float2(__double2float_rn(x), __double2float_rn(y));
+}
+__device__ __forceinline__ float2 div_fast(float2 n, float2 h)
+{
+    float inv = 1.0f / fmaf(h.x, h.x, h.y * h.y);
+    return make_float2(fmaf(n.x, h.x, n.y * h.y) * inv, fmaf(n.y, h.x, -n.x * h.y) * inv);
+}
+
+template <bool EXACT, int NOISE>
+__global__ void __launch_bounds__(kThreads) k_rx_frames(RxParams p)
+{
+    __shared__ float2 s_tile[kWarpsPerBlock][kWarpTile];
+    __shared__ float2 s_lts[kWarpsPerBlock][2][64];
+    __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
+    __shared__ double s_sum[kWarpsPerBlock][3];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    const uint32_t grp_mask = 0xFFu << (grp * 8);
+    float2 *tile = s_tile[warp] + grp * kGroupPitch;
+    Tw<EXACT> tw; tw.load(u);
+    int dmap[8]; float hsc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        dmap[j] = c_tab.bin_data[u + 8 * j];
+        hsc[j] = 0.5f * (float)c_tab.bin_lts[u + 8 * j];        // 0.5 * conj(L), L real: exact scaling, OFDM.c:848
+    }
+    const int n_sym = p.n_sym, len = 160 + 80 * n_sym;
+    const int n_pass = 1 + (n_sym > 2 ? (n_sym - 2 + 3) / 4 : 0);
+    const double q = (double)kQpsk;
+    const double ref2_frame = 48.0 * n_sym * (2.0 * q * q);     // sum |tx|^2 over the frame's data bins
+
+    unsigned long long a_bit = 0, a_rail = 0, a_ferr = 0, a_frames = 0;
+    double a_e2 = 0.0, a_ref2 = 0.0, a_evm = 0.0;
+
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < p.n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float2 *x = p.in + f * len;
+        double sigma_d = 0.0; float sigma_f = 0.f;
+        if (NOISE != kNoiseNone) {
+            float np = __fdiv_rn(p.power[f], p.snr_lin);
+            sigma_d = __dsqrt_rn((double)np);
+            sigma_f = (float)sigma_d;
+        }
+        float2 H[8];
+        uint32_t f_bit = 0, f_rail = 0;
+        double f_e2 = 0.0;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int sym = pass == 0 ? grp - 2 : 2 + (pass - 1) * 4 + grp;     // < 0: LTS half
+            const bool active = sym < n_sym;
+            const int n0 = sym < 0 ? 32 + 64 * grp : 176 + 80 * sym;           // Channel_Estimation :837-838, CP strip :1028
+            float2 v[8];
+            float z[8];
+            if (NOISE == kNoisePhilox && active) {
+                int base = window_block_base(n0) + u;
+                float za[4], zb[4];
+                philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)base, kDomainNoise, za);
+                philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)(base + 8), kDomainNoise, zb);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = slot_m<EXACT>(i);
+                float2 s = make_float2(0.f, 0.f);
+                if (active) {
+                    s = x[n0 + u + 8 * m];
+                    if (NOISE == kNoiseInject) s.x = add_noise<EXACT>(s.x, p.g[f * len + n0 + u + 8 * m], sigma_d, sigma_f);
+                    if (NOISE == kNoisePhilox) s.x = add_noise<EXACT>(s.x, z[m], sigma_d, sigma_f);
+                }
+                v[i] = s;
+            }
+            fft64<EXACT>(v, tw, tile, u);                                       // natural bins u + 8j
+            if (pass == 0) {
+                if (grp < 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s_lts[warp][grp][u + 8 * j] = v[j];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                                   // H = 0.5*(A+B)*conj(L)  :848
+                    float2 A = s_lts[warp][0][u + 8 * j], B = s_lts[warp][1][u + 8 * j];
+                    H[j] = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), hsc[j]), __fmul_rn(__fadd_rn(A.y, B.y), hsc[j]));
+                }
+                if (p.dump.H != nullptr && grp == 0) {
+                    float2 *Hout = reinterpret_cast<float2 *>(p.dump.H) + f * 64;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) Hout[(u + 8 * j + 32) & 63] = H[j];
+                }
+                __syncwarp();
+            }
+            if (active && sym >= 0) {
+                const uint32_t *w = p.tx_bits + (f * n_sym + sym) * 3;
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                uint32_t o0 = 0, o1 = 0, o2 = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int d = dmap[j];
+                    if (d < 0) continue;                                        // demap :1063-1068 keeps the 48 data bins
+                    float2 E = EXACT ? div_exact(v[j], H[j]) : div_fast(v[j], H[j]);   // :1050
+                    const bool re_pos = E.x > 0.f, im_pos = E.y > 0.f;          // AGC_Receiver :860-868
+                    const uint32_t rx = demod_pair(re_pos, im_pos);             // QPSK_Demodulator :883-902
+                    const uint32_t txp = bit_pair(w0, w1, w2, d);
+                    const float2 t = qpsk_point(txp);
+                    f_bit += __popc(rx ^ txp);                                  // BER :1158
+                    f_rail += (uint32_t)(re_pos != (t.x > 0.f)) + (uint32_t)(im_pos != (t.y > 0.f));
+                    const double er = (double)E.x - (double)t.x, ei = (double)E.y - (double)t.y;
+                    f_e2 += er * er + ei * ei;                                  // EVM :1114-1115
+                    if (p.dump.eq != nullptr)
+                        reinterpret_cast<float2 *>(p.dump.eq)[(f * n_sym + sym) * 48 + d] = E;
+                    if (p.dump.sliced != nullptr)
+                        reinterpret_cast<float2 *>(p.dump.sliced)[(f * n_sym + sym) * 48 + d] =
+                            make_float2(re_pos ? kQpsk : -kQpsk, im_pos ? kQpsk : -kQpsk);
+                    const uint32_t sh = rx << (2 * (d & 15));
+                    if (d < 16) o0 |= sh; else if (d < 32) o1 |= sh; else o2 |= sh;
+                }
+                if (p.dump.bits != nullptr) {
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        o0 |= __shfl_xor_sync(grp_mask, o0, o);
+                        o1 |= __shfl_xor_sync(grp_mask, o1, o);
+                        o2 |= __shfl_xor_sync(grp_mask, o2, o);
+                    }
+                    if (u == 0) { uint32_t *ob = p.dump.bits + (f * n_sym + sym) * 3; ob[0] = o0; ob[1] = o1; ob[2] = o2; }
+                }
+            }
+            __syncwarp();
+        }
+        f_bit = warp_sum(f_bit);
+        f_rail = warp_sum(f_rail);
+        f_e2 = warp_sum(f_e2);
+        if (lane == 0) {
+            const double evm = sqrt(f_e2 / ref2_frame);                         // :1124
+            if (p.dump.frame_bit_errors != nullptr) p.dump.frame_bit_errors[f] = (int32_t)f_bit;
+            if (p.dump.frame_evm_lin != nullptr) p.dump.frame_evm_lin[f] = (float)evm;
+            a_bit += f_bit; a_rail += f_rail; a_ferr += f_bit != 0; a_frames += 1;
+            a_e2 += f_e2; a_ref2 += ref2_frame; a_evm += evm;
+        }
+    }
+    if (p.counters == nullptr) return;
+    if (lane == 0) {
+        s_cnt[warp][0] = a_bit; s_cnt[warp][1] = a_rail; s_cnt[warp][2] = a_ferr; s_cnt[warp][3] = a_frames;
+        s_sum[warp][0] = a_e2; s_sum[warp][1] = a_ref2; s_sum[warp][2] = a_evm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long c[4] = {0, 0, 0, 0}; double s[3] = {0, 0, 0};
+        for (int w = 0; w < kWarpsPerBlock; ++w) {
+            for (int k = 0; k < 4; ++k) c[k] += s_cnt[w][k];
+            for (int k = 0; k < 3; ++k) s[k] += s_sum[w][k];
+        }
+        if (c[3] != 0) {
+            ofdm_counters *o = p.counters;
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->bit_errors), c[0]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->rail_errors), c[1]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames_in_error), c[2]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames), c[3]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->bits), c[3] * 96ull * (unsigned long long)n_sym);
+            atomicAdd(&o->sum_err2, s[0]);
+            atomicAdd(&o->sum_ref2, s[1]);
+            atomicAdd(&o->sum_evm_lin, s[2]);
+        }
+    }
+}
+
+}  // namespace ofdm

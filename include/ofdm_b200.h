@@ -1,0 +1,174 @@
+/*
+ * ofdm_b200.h -- C-ABI of libofdm_b200.so: the B200-native (sm_100a) 802.11a OFDM QPSK
+ * TX -> AWGN -> RX stage chain.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (Unalome81/IEEE-802.11-OFDM-QPSK-Simulator) has no FFI: its "stage interface"
+ * is the set of C functions in src/OFDM.c called from main().  Each entry point below is the
+ * batched, re-entrant replacement of one of those functions or inline blocks (cited as
+ * OFDM.c:line), plus fused entry points that run several stages in one kernel.  Differences
+ * that are deliberate and uniform:
+ *   - an explicit context handle instead of the reference's globals (OFDM.c:24-34);
+ *   - int status returns instead of exit(1)/perror (OFDM.c:150-153, :97-100);
+ *   - caller-owned flat buffers [frames][samples] instead of callee-allocated row pointers;
+ *   - IQ is interleaved (re, im) float pairs == the memory layout of C `float complex`;
+ *   - payload bits are packed, 96 bits per OFDM symbol = 3 little-endian uint32 words
+ *     (bit j of a symbol = bit (j & 31) of word j >> 5); ofdm_pack_bits/ofdm_unpack_bits convert
+ *     from/to the one-value-per-bit layout the reference uses (it stores bits as float complex);
+ *   - frame = LTS(160 samples) || n_sym x (16-sample CP + 64): the reference's 480-sample frame
+ *     (OFDM.c:569-581) minus the 160-sample STS slot, which only detection/coarse CFO use.
+ *
+ * Pointers documented "device" are CUDA device pointers (from ofdm_dev_alloc or any CUDA
+ * allocator, e.g. a torch tensor's data_ptr); "host" pointers are ordinary memory.  All device
+ * work is enqueued on the context's stream; entry points that return results to host memory
+ * synchronise that stream before returning.  There is no CPU fallback anywhere.
+ *
+ * mode: OFDM_MODE_EXACT reproduces the reference's arithmetic bit for bit (double twiddle
+ * products rounded to float, float add/sub, double-widened complex division; SURVEY.md
+ * section 7); OFDM_MODE_FAST is the fp32 radix-8 path (1e-5 relative on IQ / EVM).
+ */
+#ifndef OFDM_B200_H
+#define OFDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDM_B200_VERSION 100
+
+enum {
+    OFDM_OK = 0,
+    OFDM_ERR_INVALID = 1,    /* bad argument (null pointer, n_sym < 1, unknown mode ...) */
+    OFDM_ERR_CUDA = 2,       /* a CUDA runtime call failed; see ofdm_last_error() */
+    OFDM_ERR_NOMEM = 3,      /* host or device allocation failed (reference: exit(1), OFDM.c:152) */
+    OFDM_ERR_IO = 4,         /* fopen/fwrite failed (reference: perror + return, OFDM.c:97-100) */
+    OFDM_ERR_NODEVICE = 5    /* no CUDA device: there is NO CPU fallback */
+};
+
+enum { OFDM_MODE_EXACT = 0, OFDM_MODE_FAST = 1 };
+
+#define OFDM_NFFT 64
+#define OFDM_CP 16
+#define OFDM_SYM_LEN 80          /* CP + NFFT */
+#define OFDM_LTS_LEN 160
+#define OFDM_DATA_PER_SYM 48
+#define OFDM_BITS_PER_SYM 96
+#define OFDM_WORDS_PER_SYM 3
+#define OFDM_MAX_SYM 512
+#define OFDM_FRAME_LEN(n_sym) (OFDM_LTS_LEN + OFDM_SYM_LEN * (n_sym))
+
+typedef struct ofdm_ctx ofdm_ctx;
+
+/* Cross-frame totals for one SNR point.  The reference's Res[3] (OFDM.c:1163-1165) is defined
+ * per frame with float accumulators that stall at 2^24; batches use integer
+ * and double totals and ofdm_counters_finalize() turns them back into {EVM_dB, EVM_AGC_dB, BER}. */
+typedef struct {
+    uint64_t bit_errors;        /* sum |tx_bit - rx_bit|                         OFDM.c:1156-1159 */
+    uint64_t bits;              /* 96 * n_sym * frames                                            */
+    uint64_t frames_in_error;   /* frames with >= 1 bit error                                     */
+    uint64_t rail_errors;       /* I/Q rails whose slicer output != tx rail      OFDM.c:1134-1142 */
+    uint64_t frames;
+    double sum_err2;            /* sum |equalised - tx|^2 over data bins         OFDM.c:1114-1115 */
+    double sum_ref2;            /* sum |tx|^2 over data bins                     OFDM.c:1116      */
+    double sum_evm_lin;         /* sum over frames of the per-frame linear EVM   OFDM.c:1124      */
+} ofdm_counters;
+
+/* Optional per-frame / per-bin outputs of the receiver (device pointers, any may be NULL). */
+typedef struct {
+    float *H;                   /* [frames][64][2]        channel estimate, centred order  OFDM.c:848        */
+    float *eq;                  /* [frames][n_sym*48][2]  equalised data bins              OFDM.c:1050,:1063 */
+    float *sliced;              /* [frames][n_sym*48][2]  "AGC" slicer output              OFDM.c:852        */
+    uint32_t *bits;             /* [frames][n_sym*3]      demodulated bits, packed         OFDM.c:873        */
+    int32_t *frame_bit_errors;  /* [frames]                                                                  */
+    float *frame_evm_lin;       /* [frames]               per-frame EVM before the slicer  OFDM.c:1124       */
+} ofdm_rx_dump;
+
+/* ---- context, errors, memory ---------------------------------------------------------------- */
+int ofdm_version(void);
+const char *ofdm_strerror(int status);
+int ofdm_ctx_create(ofdm_ctx **ctx, int device);
+int ofdm_ctx_destroy(ofdm_ctx *ctx);
+const char *ofdm_last_error(const ofdm_ctx *ctx);
+int ofdm_ctx_set_stream(ofdm_ctx *ctx, void *cuda_stream);   /* run on a caller-owned cudaStream_t */
+void *ofdm_ctx_stream(const ofdm_ctx *ctx);
+int ofdm_ctx_sync(ofdm_ctx *ctx);
+int ofdm_ctx_sm_count(const ofdm_ctx *ctx);
+uint64_t ofdm_ctx_launch_count(const ofdm_ctx *ctx);          /* kernels launched so far by this ctx */
+int ofdm_dev_alloc(ofdm_ctx *ctx, void **ptr, size_t bytes);
+int ofdm_dev_free(ofdm_ctx *ctx, void *ptr);
+int ofdm_host_alloc(ofdm_ctx *ctx, void **ptr, size_t bytes);   /* pinned host memory */
+int ofdm_host_free(ofdm_ctx *ctx, void *ptr);
+int ofdm_memcpy_h2d(ofdm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* async on the stream */
+int ofdm_memcpy_d2h(ofdm_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);   /* async on the stream */
+int ofdm_memset_dev(ofdm_ctx *ctx, void *dst_dev, int value, size_t bytes);
+
+/* ---- stage-level entry points (device buffers) ---------------------------------------------- */
+/* layout helpers: one byte per bit <-> packed words */
+int ofdm_pack_bits(ofdm_ctx *ctx, const uint8_t *bits_dev, uint32_t *packed_dev, long n_symbols);
+int ofdm_unpack_bits(ofdm_ctx *ctx, const uint32_t *packed_dev, uint8_t *bits_dev, long n_symbols);
+/* QPSK_Modulator, OFDM.c:415-433: n_symbols x 96 bits -> [n_symbols][48] points */
+int ofdm_qpsk_modulate(ofdm_ctx *ctx, const uint32_t *bits_dev, float *mod_dev, long n_symbols);
+/* inline frame build, OFDM.c:523-548: [n_symbols][48] -> centred [n_symbols][64] grid, pilots +1,+1,+1,-1 */
+int ofdm_map_subcarriers(ofdm_ctx *ctx, const float *mod_dev, float *grid_dev, long n_symbols);
+/* ifft, OFDM.c:320-339: centred input, output rotated by 32 samples exactly as the reference's */
+int ofdm_ifft64(ofdm_ctx *ctx, const float *in_dev, float *out_dev, long n, int mode);
+/* fft, OFDM.c:314-318: centred (fft_shift'ed) output */
+int ofdm_fft64(ofdm_ctx *ctx, const float *in_dev, float *out_dev, long n, int mode);
+/* CP add, OFDM.c:559-565: [n][64] -> [n][80] */
+int ofdm_add_cp(ofdm_ctx *ctx, const float *sym_dev, float *out_dev, long n);
+/* Preamble_Generator(type=1), OFDM.c:368-399: host copies of the LTS, frequency (centred, 64) and time (160) */
+int ofdm_lts(ofdm_ctx *ctx, float *lts_freq_host, float *lts_time_host);
+/* Transmitter OFDM.c:500-581 without STS/RRC: bits -> frames [n_frames][160+80*n_sym]; power_dev
+ * (nullable, [n_frames]) receives the per-frame mean power of OFDM.c:637-643 */
+int ofdm_tx_frames(ofdm_ctx *ctx, const uint32_t *bits_dev, float *frames_dev, float *power_dev,
+                   long n_frames, int n_sym, int mode);
+/* signal-power block of Transmission_Over_Air, OFDM.c:637-643 (float accumulator, sequential, in EXACT) */
+int ofdm_frame_power(ofdm_ctx *ctx, const float *frames_dev, float *power_dev, long n_frames, int frame_len, int mode);
+/* Transmission_Over_Air, OFDM.c:635-655, real-rail noise only, per-frame power.
+ * _inject: the standard-normal draw per sample is supplied (g_dev [n_frames][frame_len]);
+ * _philox: drawn on chip, key (seed, stream), counter (frame0 + frame, block, domain).
+ * power_dev may be NULL (computed internally). */
+int ofdm_awgn_inject(ofdm_ctx *ctx, const float *tx_dev, const float *g_dev, const float *power_dev, float snr_db,
+                     float *ota_dev, long n_frames, int n_sym, int mode);
+int ofdm_awgn_philox(ofdm_ctx *ctx, const float *tx_dev, const float *power_dev, float snr_db, uint32_t seed,
+                     uint32_t stream, uint64_t frame0, float *ota_dev, long n_frames, int n_sym, int mode);
+/* Receiver OFDM.c:1018-1165 on LTS||data frames: Channel_Estimation :830, CP strip :1024, fft :1037,
+ * equalise :1046, demap :1061, AGC_Receiver :852, QPSK_Demodulator :873, EVM :1106-1150, BER :1154.
+ * counters_dev (device, one ofdm_counters, accumulated into -- zero it first) may be NULL. */
+int ofdm_rx_frames(ofdm_ctx *ctx, const float *ota_dev, const uint32_t *tx_bits_dev, long n_frames, int n_sym,
+                   int mode, ofdm_counters *counters_dev, const ofdm_rx_dump *dump);
+/* fused channel + receiver: reads TX frames, adds the noise in registers, never writes OTA IQ */
+int ofdm_awgn_rx_inject(ofdm_ctx *ctx, const float *tx_dev, const float *g_dev, const float *power_dev,
+                        const uint32_t *tx_bits_dev, float snr_db, long n_frames, int n_sym, int mode,
+                        ofdm_counters *counters_dev, const ofdm_rx_dump *dump);
+int ofdm_awgn_rx_philox(ofdm_ctx *ctx, const float *tx_dev, const float *power_dev, const uint32_t *tx_bits_dev,
+                        float snr_db, uint32_t seed, uint32_t stream, uint64_t frame0, long n_frames, int n_sym,
+                        int mode, ofdm_counters *counters_dev, const ofdm_rx_dump *dump);
+
+/* ---- sweep drivers: host buffers in, host counters out (what main()'s loop OFDM.c:1202-1222 does) ---- */
+/* Transmitter once, then per SNR point channel + receiver, injected normals reused across points
+ * (only the scale changes).  bits_host [n_frames][n_sym*3] packed; g_host [n_frames][frame_len];
+ * out_host [n_snr].  H2D copies, kernels and the D2H of the counters all run inside the call. */
+int ofdm_sweep_inject_host(ofdm_ctx *ctx, const uint32_t *bits_host, const float *g_host, long n_frames, int n_sym,
+                           const float *snr_db, int n_snr, int mode, ofdm_counters *out_host);
+/* same with resident device buffers (no copies except the counters) */
+int ofdm_sweep_inject_dev(ofdm_ctx *ctx, const uint32_t *bits_dev, const float *g_dev, long n_frames, int n_sym,
+                          const float *snr_db, int n_snr, int mode, ofdm_counters *out_host);
+
+/* Res[3] = {EVM_dB, EVM_AGC_dB, BER} of OFDM.c:1163-1165 from batch totals */
+int ofdm_counters_finalize(const ofdm_counters *c, float res[3]);
+
+/* ---- result / dump writers (host) ------------------------------------------------------------- */
+/* write_float_array_to_file, OFDM.c:123-143: one line, tab-separated %.2e */
+int ofdm_write_float_array_to_file(const float *a, int n, const char *fname);
+/* write_complex_array_to_file, OFDM.c:94-121.  format 0 = what the reference writes today (real parts
+ * only, %.15e, tab-separated; compare_double.py reads it); format 1 = the commented-out line :105 with
+ * blanks ("re + imi" / "re - imi" triples, the layout compare_complex.py parses).  SURVEY Q12. */
+int ofdm_write_complex_array_to_file(const float *a_iq, int n, const char *fname, int format);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

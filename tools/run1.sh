@@ -1,0 +1,4 @@
+cd $GRAFT_REPO_ROOT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -40
+python __graft_entry__.py smoke 2>&1 | tail -5
