@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- OFDM symbols/s through the TX -> AWGN -> RX chain (BASELINE.json metric).
+
+Workload (configs[1]): batched QPSK BER/EVM sweep, 1,000,000 frames x 2 data symbols, 21 SNR points
+0..20 dB, injected standard-normal draws (one per sample, reused across SNR points), EXACT mode
+(bit-exact error counts versus OFDM.c).  One "step" = one whole sweep: Transmitter once, then per SNR
+point the fused channel+receiver kernel.  A counted OFDM symbol is one data symbol that went through
+TX, the channel and RX at one SNR point: symbols/step = frames x n_sym x n_snr.
+
+  value   inputs resident in HBM, CUDA-event timed on the launching stream
+  e2e     the same sweep through ofdm_sweep_inject_host: HOST (pinned) bits + draws, H2D copies,
+          kernels and the D2H of the counters inside the timed region
+  roofline  dominant kernel k_rx_frames<exact,inject>: algorithmic bytes (3100 B per frame and SNR
+            point) / mean launch time (CUDA events around each launch in the timed region)
+  cpu_baseline  the compiled reference (oracle/_ref) stage chain on a bounded sample, one thread
+
+--impl reference: the reference's own CPU implementation of the path (oracle/_ref, else the oracle
+port) on all host cores, each step a bounded sample of the same workload.
+Multi-GPU (torchrun): frames are sharded across ranks (weak scaling: 1M frames per rank), one NCCL
+all-reduce of the counters per sweep; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+N_SYM = 2
+SNRS = [float(s) for s in range(0, 21)]
+BYTES_PER_FRAME_PASS = (128 + 64 * N_SYM) * 8 + (128 + 64 * N_SYM) * 4 + 12 * N_SYM + 4   # 3100
+METRIC = "OFDM symbols/s, TX+AWGN+RX chain (BER/EVM sweep)"
+UNIT = "symbols/s"
+
+
+def workload_name(n_frames):
+    return ("cfg1: batched QPSK BER/EVM sweep, %d frames x %d data symbols x %d SNR points (0..20 dB), "
+            "injected normals, exact mode" % (n_frames, N_SYM, len(SNRS)))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(self.NAMES, r[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference legs
+_W = {}
+
+
+def _worker_init():
+    po = entry.load_oracle()
+    _W["impl"] = po.Ref() if po.have_ref() else po.Port()
+
+
+def _worker_run(args):
+    bits, g, snrs = args
+    impl = _W["impl"]
+    tot = 0
+    for s in snrs:
+        tot += impl.chain(bits, g, N_SYM, s).bit_errors
+    return tot
+
+
+def sample_inputs(n_frames, seed):
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, (n_frames, 96 * N_SYM), dtype=np.uint8)
+    g = rng.standard_normal((n_frames, 160 + 80 * N_SYM)).astype(np.float32)
+    return bits, g
+
+
+def cpu_baseline_single(sample_frames):
+    """oracle/_ref (kind reference) or the port, one thread, bounded sample of the same workload."""
+    po = entry.load_oracle()
+    po.build()
+    kind = "reference" if po.have_ref() else "port"
+    impl = po.Ref() if kind == "reference" else po.Port()
+    bits, g = sample_inputs(sample_frames, 1234)
+    impl.chain(bits[:64], g[:64], N_SYM, 10.0)          # warm
+    t0 = time.perf_counter()
+    for s in SNRS:
+        impl.chain(bits, g, N_SYM, s)
+    dt = time.perf_counter() - t0
+    return {"value": sample_frames * N_SYM * len(SNRS) / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "%d frames x %d symbols x %d SNR points, injected normals, %.1f s" % (sample_frames, N_SYM, len(SNRS), dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    po = entry.load_oracle()
+    po.build()
+    kind = "reference" if po.have_ref() else "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_core = 192
+    n_frames = per_core * cores
+    bits, g = sample_inputs(n_frames, 4321)
+    tasks = [(bits[i * per_core:(i + 1) * per_core], g[i * per_core:(i + 1) * per_core], SNRS) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_worker_init) as pool:
+        for _ in range(args.warmup):
+            pool.map(_worker_run, tasks, chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_worker_run, tasks, chunksize=1)
+        dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = n_frames * N_SYM * len(SNRS) / (dt / args.steps)
+    sample = "%d frames x %d symbols x %d SNR points per step, %d processes" % (n_frames, N_SYM, len(SNRS), cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.frames), "reference_arm_sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = entry.load_pkg()
+    o = pkg.Ofdm(local)
+    n_frames, n_snr = args.frames, len(SNRS)
+    flen = pkg.frame_len(N_SYM)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n_frames * N_SYM * 3,), dtype=torch.int32, device=dev, generator=gen)
+    g = torch.randn((n_frames, flen), dtype=torch.float32, device=dev, generator=gen)
+    frames = torch.empty((n_frames, flen, 2), dtype=torch.float32, device=dev)
+    power = torch.empty((n_frames,), dtype=torch.float32, device=dev)
+    counters = o.new_counters(n_snr)
+    host_cnt = torch.empty(counters.shape, dtype=torch.int64).pin_memory()
+    bits_h = torch.empty(bits.shape, dtype=torch.int32).pin_memory(); bits_h.copy_(bits)
+    g_h = torch.empty(g.shape, dtype=torch.float32).pin_memory(); g_h.copy_(g)
+    torch.cuda.synchronize()
+    lib, h = o.lib, o.h
+    kernel_ms = []
+
+    def sweep_resident(record):
+        counters.zero_()
+        o._check(lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), power.data_ptr(), n_frames, N_SYM, pkg.MODE_EXACT))
+        evs = []
+        for i, s in enumerate(SNRS):
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+            o._check(lib.ofdm_awgn_rx_inject(h, frames.data_ptr(), g.data_ptr(), power.data_ptr(), bits.data_ptr(), s,
+                                             n_frames, N_SYM, pkg.MODE_EXACT, counters[i].data_ptr(), None))
+            if record:
+                e1.record(); evs.append((e0, e1))
+        if world > 1:
+            ints = counters[:, :5].contiguous(); dist.all_reduce(ints); counters[:, :5] = ints          # integer totals
+            fl = counters[:, 5:].contiguous().view(torch.float64); dist.all_reduce(fl)                   # double sums
+            counters[:, 5:] = fl.view(torch.int64)
+        host_cnt.copy_(counters, non_blocking=True)
+        return evs
+
+    def sweep_host():
+        res = o.sweep_inject_host(bits_h, g_h, n_frames, N_SYM, SNRS, pkg.MODE_EXACT)
+        if world > 1:
+            t = torch.tensor([[c.bit_errors, c.bits, c.frames_in_error, c.rail_errors, c.frames] for c in res],
+                             dtype=torch.int64, device=dev)
+            dist.all_reduce(t)
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        sweep_resident(False)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = o.launch_count
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    all_evs = []
+    for _ in range(args.steps):
+        all_evs += sweep_resident(True)
+    t1.record()
+    barrier()
+    launches = o.launch_count - launches0
+    ms_total = t0.elapsed_time(t1)
+    kernel_ms = [a.elapsed_time(b) for a, b in all_evs]
+    resident_counts = o.read_counters(host_cnt)
+
+    # end to end through the public host-buffer API
+    for _ in range(max(1, args.warmup // 2)):
+        sweep_host()
+    barrier()
+    w0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_counts = sweep_host()
+    e1.record()
+    barrier()
+    e2e_ms_total = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)   # wall clock covers the host side of the call
+    clocks = sampler.stop() if rank == 0 else None
+
+    tm = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = tm.tolist()
+    if rank == 0:
+        # the two paths must agree on every integer total (single GPU: same frames)
+        if world == 1:
+            for a, b in zip(resident_counts, e2e_counts):
+                assert (a.bit_errors, a.rail_errors, a.frames_in_error) == (b.bit_errors, b.rail_errors, b.frames_in_error)
+        symbols = n_frames * N_SYM * n_snr * world
+        ms_step = ms_total / args.steps
+        value = symbols / (ms_step * 1e-3)
+        e2e_value = symbols / (e2e_ms_total / args.steps * 1e-3)
+        k_ms = float(np.mean(kernel_ms))
+        peak, peak_src = peaks()
+        achieved = BYTES_PER_FRAME_PASS * n_frames / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("k_rx_frames_exact_inject_bytes_per_launch")
+        ber = [c.bit_errors / max(1, c.bits) for c in resident_counts]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": workload_name(n_frames), "frames_per_gpu": n_frames, "n_sym": N_SYM, "snr_db": [SNRS[0], SNRS[-1]],
+                           "mode": "exact", "l2": "inputs larger than L2 (%.2f GB of draws + %.2f GB of TX IQ per sweep)"
+                                                   % (g.numel() * 4 / 1e9, frames.numel() * 4 / 1e9),
+                           "parallelism": "frames sharded across %d GPU(s), one NCCL all-reduce of the counters" % world},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_total / args.steps,
+                        "h2d_bytes_per_step": int(bits_h.numel() * 4 + g_h.numel() * 4),
+                        "d2h_bytes_per_step": int(n_snr * pkg.COUNTERS_BYTES)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_rx_frames<exact,inject>", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "bytes_per_launch": BYTES_PER_FRAME_PASS * n_frames, "kernel_ms": k_ms,
+                             "kernel_share_of_step": k_ms * n_snr / ms_step},
+                "clocks": clocks,
+                "ber_0_10_20dB": [ber[0], ber[10], ber[20]]}
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
+        print(json.dumps(line), flush=True)
+    o.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1_000_000, help="frames per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=4000, help="frames in the single-thread CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -131,25 +131,33 @@ int launch_fft(ofdm_ctx *ctx, const float *in, float *out, long n)
     return check_launch(ctx, "k_fft64");
 }
 
-template <bool EXACT, int NOISE>
+template <bool EXACT, int NOISE, bool DUMP>
 int launch_rx(ofdm_ctx *ctx, const RxParams &p)
 {
-    auto k = k_rx_frames<EXACT, NOISE>;
+    auto k = k_rx_frames<EXACT, NOISE, DUMP>;
     int grid = grid_for(ctx, k, 0, kWarpsPerBlock, p.n_frames);
     k<<<grid, kThreads, 0, ctx->stream>>>(p);
     return check_launch(ctx, "k_rx_frames");
 }
 
+template <bool EXACT, int NOISE>
+int launch_rx_d(ofdm_ctx *ctx, bool dump, const RxParams &p)
+{
+    return dump ? launch_rx<EXACT, NOISE, true>(ctx, p) : launch_rx<EXACT, NOISE, false>(ctx, p);
+}
+
 int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
 {
+    const ofdm_rx_dump &d = p.dump;
+    const bool dump = d.H || d.eq || d.sliced || d.bits || d.frame_bit_errors || d.frame_evm_lin;
     if (mode == OFDM_MODE_EXACT) {
-        if (noise == kNoiseNone) return launch_rx<true, kNoiseNone>(ctx, p);
-        if (noise == kNoiseInject) return launch_rx<true, kNoiseInject>(ctx, p);
-        return launch_rx<true, kNoisePhilox>(ctx, p);
+        if (noise == kNoiseNone) return launch_rx_d<true, kNoiseNone>(ctx, dump, p);
+        if (noise == kNoiseInject) return launch_rx_d<true, kNoiseInject>(ctx, dump, p);
+        return launch_rx_d<true, kNoisePhilox>(ctx, dump, p);
     }
-    if (noise == kNoiseNone) return launch_rx<false, kNoiseNone>(ctx, p);
-    if (noise == kNoiseInject) return launch_rx<false, kNoiseInject>(ctx, p);
-    return launch_rx<false, kNoisePhilox>(ctx, p);
+    if (noise == kNoiseNone) return launch_rx_d<false, kNoiseNone>(ctx, dump, p);
+    if (noise == kNoiseInject) return launch_rx_d<false, kNoiseInject>(ctx, dump, p);
+    return launch_rx_d<false, kNoisePhilox>(ctx, dump, p);
 }
 
 int frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames, int len, int mode)

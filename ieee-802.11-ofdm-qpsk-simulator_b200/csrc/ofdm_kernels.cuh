@@ -282,31 +282,80 @@ __device__ __forceinline__ float2 div_fast(float2 n, float2 h)
     return make_float2(fmaf(n.x, h.x, n.y * h.y) * inv, fmaf(n.y, h.x, -n.x * h.y) * inv);
 }
 
-template <bool EXACT, int NOISE>
-__global__ void __launch_bounds__(kThreads) k_rx_frames(RxParams p)
+// One data bin through equalise :1050, slicer :860-868, demod :883-902, BER :1158 and the EVM terms :1114.
+// Returns the rail-error flags (bit0 = I rail, bit1 = Q rail).  Bit errors follow from the non-Gray map
+// (SURVEY Q5): a Q-rail error flips bit a, and bit b flips when exactly one rail is wrong.
+//
+// EXACT, no dump: the decision is the sign of the float(num/den) the reference computes.  For normal
+// magnitudes that is the sign of the exact numerator a*c+b*d (resp. b*c-a*d); the fp32 evaluation is
+// trusted only when it is at least 2^-20 of the magnitude bound m (its error is < 2^-23 m) and m, den
+// sit in [1e-15, 1e15] (no float under/overflow of the quotient); everything else takes the exact
+// double-widened division.  The EVM terms use the fp32 quotient (1e-5 contract).
+template <bool EXACT, bool DUMP>
+__device__ __forceinline__ uint32_t process_bin(float2 F, float2 Hh, uint32_t txp, float &e2, float2 &E_out, bool &re_pos, bool &im_pos)
+{
+    const float a = F.x, b = F.y, c = Hh.x, d = Hh.y;
+    float2 E;
+    if (EXACT && DUMP) {
+        E = div_exact(F, Hh);
+        re_pos = E.x > 0.f; im_pos = E.y > 0.f;
+    } else {
+        const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
+        const float den = fmaf(c, c, d * d);
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+        E = make_float2(sr * inv, si * inv);
+        re_pos = sr > 0.f; im_pos = si > 0.f;
+        if (EXACT) {
+            const float m = (fabsf(a) + fabsf(b)) * (fabsf(c) + fabsf(d));
+            const float lim = 1e-6f * m;
+            const bool safe = fabsf(sr) > lim && fabsf(si) > lim && fminf(m, den) > 1e-15f && fmaxf(m, den) < 1e15f;
+            if (!safe) {
+                E = div_exact(F, Hh);
+                re_pos = E.x > 0.f; im_pos = E.y > 0.f;
+            }
+        }
+    }
+    const uint32_t A = txp & 1u, B = txp >> 1;
+    const bool i_pos = (A ^ B) == 0u, q_pos = A == 0u;           // tx rails, QPSK_Modulator :423-430
+    const float er = E.x - (i_pos ? kQpsk : -kQpsk), ei = E.y - (q_pos ? kQpsk : -kQpsk);
+    e2 = fmaf(er, er, fmaf(ei, ei, e2));
+    E_out = E;
+    return (uint32_t)(re_pos != i_pos) | ((uint32_t)(im_pos != q_pos) << 1);
+}
+
+// Fused receiver.  DUMP = false is the sweep path: totals only, bins of the two first data symbols
+// are shared with the (otherwise idle) LTS lane groups so all 32 lanes work through the decision
+// stage.  DUMP = true writes any of the per-bin / per-frame outputs and always divides exactly.
+template <bool EXACT, int NOISE, bool DUMP>
+__global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p)
 {
     __shared__ float2 s_tile[kWarpsPerBlock][kWarpTile];
-    __shared__ float2 s_lts[kWarpsPerBlock][2][64];
+    __shared__ float2 s_lts[kWarpsPerBlock][2][72];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
-    __shared__ double s_sum[kWarpsPerBlock][3];
+    __shared__ double s_sum[kWarpsPerBlock][2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
     const uint32_t grp_mask = 0xFFu << (grp * 8);
     float2 *tile = s_tile[warp] + grp * kGroupPitch;
     Tw<EXACT> tw; tw.load(u);
-    int dmap[8]; float hsc[8];
+    // per-lane bin info for natural bins u + 8j, one byte each: data index, or >= 0x80 for null / pilot
+    uint32_t dlo = 0, dhi = 0, lneg = 0, lnul = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        dmap[j] = c_tab.bin_data[u + 8 * j];
-        hsc[j] = 0.5f * (float)c_tab.bin_lts[u + 8 * j];        // 0.5 * conj(L), L real: exact scaling, OFDM.c:848
+        const uint32_t d = (uint32_t)(uint8_t)c_tab.bin_data[u + 8 * j];
+        if (j < 4) dlo |= d << (8 * j); else dhi |= d << (8 * (j - 4));
+        const int l = c_tab.bin_lts[u + 8 * j];
+        lneg |= (uint32_t)(l < 0) << j; lnul |= (uint32_t)(l == 0) << j;
     }
     const int n_sym = p.n_sym, len = 160 + 80 * n_sym;
     const int n_pass = 1 + (n_sym > 2 ? (n_sym - 2 + 3) / 4 : 0);
     const double q = (double)kQpsk;
     const double ref2_frame = 48.0 * n_sym * (2.0 * q * q);     // sum |tx|^2 over the frame's data bins
+    const float inv_ref2 = (float)(1.0 / ref2_frame);
 
-    unsigned long long a_bit = 0, a_rail = 0, a_ferr = 0, a_frames = 0;
-    double a_e2 = 0.0, a_ref2 = 0.0, a_evm = 0.0;
+    uint32_t a_rail_i = 0, a_rail_q = 0, a_rail_both = 0, a_ferr = 0, a_frames = 0;   // per lane
+    double a_e2 = 0.0, a_evm = 0.0;                                                    // warp-uniform
 
     for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < p.n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
         const float2 *x = p.in + f * len;
@@ -317,8 +366,8 @@ __global__ void __launch_bounds__(kThreads) k_rx_frames(RxParams p)
             sigma_f = (float)sigma_d;
         }
         float2 H[8];
-        uint32_t f_bit = 0, f_rail = 0;
-        double f_e2 = 0.0;
+        uint32_t f_i = 0, f_q = 0, f_both = 0;
+        float f_e2 = 0.f;
         for (int pass = 0; pass < n_pass; ++pass) {
             const int sym = pass == 0 ? grp - 2 : 2 + (pass - 1) * 4 + grp;     // < 0: LTS half
             const bool active = sym < n_sym;
@@ -352,43 +401,62 @@ __global__ void __launch_bounds__(kThreads) k_rx_frames(RxParams p)
                 }
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {                                   // H = 0.5*(A+B)*conj(L)  :848
-                    float2 A = s_lts[warp][0][u + 8 * j], B = s_lts[warp][1][u + 8 * j];
-                    H[j] = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), hsc[j]), __fmul_rn(__fadd_rn(A.y, B.y), hsc[j]));
+                for (int j = 0; j < 8; ++j) {                                   // H = 0.5*(A+B)*conj(L)  :848 (L real: exact scaling)
+                    const float2 A = s_lts[warp][0][u + 8 * j], B = s_lts[warp][1][u + 8 * j];
+                    const float sc = ((lnul >> j) & 1u) ? 0.f : (((lneg >> j) & 1u) ? -0.5f : 0.5f);
+                    H[j] = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), sc), __fmul_rn(__fadd_rn(A.y, B.y), sc));
                 }
-                if (p.dump.H != nullptr && grp == 0) {
+                if (DUMP && p.dump.H != nullptr && grp == 0) {
                     float2 *Hout = reinterpret_cast<float2 *>(p.dump.H) + f * 64;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) Hout[(u + 8 * j + 32) & 63] = H[j];
                 }
                 __syncwarp();
             }
-            if (active && sym >= 0) {
+            if (!DUMP && pass == 0) {
+                // lanes of LTS group g take over slots 4..7 of data group g+2 (same symbol g)
+                const int dsym = grp & 1;
+                float2 X[4], Hs[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float wx = __shfl_down_sync(0xffffffffu, v[4 + k].x, 16), wy = __shfl_down_sync(0xffffffffu, v[4 + k].y, 16);
+                    X[k] = grp < 2 ? make_float2(wx, wy) : v[k];
+                    Hs[k] = grp < 2 ? H[4 + k] : H[k];
+                }
+                const uint32_t dsel = grp < 2 ? dhi : dlo;
+                if (dsym < n_sym) {
+                    const uint32_t *w = p.tx_bits + (f * n_sym + dsym) * 3;
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t d = (dsel >> (8 * k)) & 0xFFu;
+                        if (d >= 0x80u) continue;
+                        float2 E; bool rp, ip;
+                        const uint32_t e = process_bin<EXACT, false>(X[k], Hs[k], bit_pair(w0, w1, w2, (int)d), f_e2, E, rp, ip);
+                        f_i += e & 1u; f_q += e >> 1; f_both += (e == 3u);
+                    }
+                }
+            } else if (active && sym >= 0) {
                 const uint32_t *w = p.tx_bits + (f * n_sym + sym) * 3;
                 const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
                 uint32_t o0 = 0, o1 = 0, o2 = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int d = dmap[j];
-                    if (d < 0) continue;                                        // demap :1063-1068 keeps the 48 data bins
-                    float2 E = EXACT ? div_exact(v[j], H[j]) : div_fast(v[j], H[j]);   // :1050
-                    const bool re_pos = E.x > 0.f, im_pos = E.y > 0.f;          // AGC_Receiver :860-868
-                    const uint32_t rx = demod_pair(re_pos, im_pos);             // QPSK_Demodulator :883-902
-                    const uint32_t txp = bit_pair(w0, w1, w2, d);
-                    const float2 t = qpsk_point(txp);
-                    f_bit += __popc(rx ^ txp);                                  // BER :1158
-                    f_rail += (uint32_t)(re_pos != (t.x > 0.f)) + (uint32_t)(im_pos != (t.y > 0.f));
-                    const double er = (double)E.x - (double)t.x, ei = (double)E.y - (double)t.y;
-                    f_e2 += er * er + ei * ei;                                  // EVM :1114-1115
-                    if (p.dump.eq != nullptr)
-                        reinterpret_cast<float2 *>(p.dump.eq)[(f * n_sym + sym) * 48 + d] = E;
-                    if (p.dump.sliced != nullptr)
-                        reinterpret_cast<float2 *>(p.dump.sliced)[(f * n_sym + sym) * 48 + d] =
-                            make_float2(re_pos ? kQpsk : -kQpsk, im_pos ? kQpsk : -kQpsk);
-                    const uint32_t sh = rx << (2 * (d & 15));
-                    if (d < 16) o0 |= sh; else if (d < 32) o1 |= sh; else o2 |= sh;
+                    const uint32_t d = ((j < 4 ? dlo : dhi) >> (8 * (j & 3))) & 0xFFu;
+                    if (d >= 0x80u) continue;                                   // demap :1063-1068 keeps the 48 data bins
+                    float2 E; bool rp, ip;
+                    const uint32_t e = process_bin<EXACT, DUMP>(v[j], H[j], bit_pair(w0, w1, w2, (int)d), f_e2, E, rp, ip);
+                    f_i += e & 1u; f_q += e >> 1; f_both += (e == 3u);
+                    if (DUMP) {
+                        if (p.dump.eq != nullptr) reinterpret_cast<float2 *>(p.dump.eq)[(f * n_sym + sym) * 48 + d] = E;
+                        if (p.dump.sliced != nullptr)
+                            reinterpret_cast<float2 *>(p.dump.sliced)[(f * n_sym + sym) * 48 + d] =
+                                make_float2(rp ? kQpsk : -kQpsk, ip ? kQpsk : -kQpsk);
+                        const uint32_t sh = demod_pair(rp, ip) << (2 * (d & 15u));
+                        if (d < 16u) o0 |= sh; else if (d < 32u) o1 |= sh; else o2 |= sh;
+                    }
                 }
-                if (p.dump.bits != nullptr) {
+                if (DUMP && p.dump.bits != nullptr) {
 #pragma unroll
                     for (int o = 1; o < 8; o <<= 1) {
                         o0 |= __shfl_xor_sync(grp_mask, o0, o);
@@ -400,28 +468,37 @@ __global__ void __launch_bounds__(kThreads) k_rx_frames(RxParams p)
             }
             __syncwarp();
         }
-        f_bit = warp_sum(f_bit);
-        f_rail = warp_sum(f_rail);
-        f_e2 = warp_sum(f_e2);
-        if (lane == 0) {
-            const double evm = sqrt(f_e2 / ref2_frame);                         // :1124
-            if (p.dump.frame_bit_errors != nullptr) p.dump.frame_bit_errors[f] = (int32_t)f_bit;
-            if (p.dump.frame_evm_lin != nullptr) p.dump.frame_evm_lin[f] = (float)evm;
-            a_bit += f_bit; a_rail += f_rail; a_ferr += f_bit != 0; a_frames += 1;
-            a_e2 += f_e2; a_ref2 += ref2_frame; a_evm += evm;
+        // bit errors of a bin = q_err + (i_err xor q_err) = i + 2q - 2*both   (BER :1158 under the map of :423-430)
+        const uint32_t f_bit_lane = f_i + 2u * f_q - 2u * f_both;
+        const bool any_err = __any_sync(0xffffffffu, f_bit_lane != 0u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f_e2 += __shfl_xor_sync(0xffffffffu, f_e2, o);
+        const float evm = sqrtf(f_e2 * inv_ref2);                               // :1124
+        if (DUMP) {
+            const uint32_t f_bit = warp_sum(f_bit_lane);
+            if (lane == 0) {
+                if (p.dump.frame_bit_errors != nullptr) p.dump.frame_bit_errors[f] = (int32_t)f_bit;
+                if (p.dump.frame_evm_lin != nullptr) p.dump.frame_evm_lin[f] = evm;
+            }
         }
+        a_rail_i += f_i; a_rail_q += f_q; a_rail_both += f_both;
+        a_ferr += any_err; a_frames += 1;
+        a_e2 += (double)f_e2; a_evm += (double)evm;
     }
     if (p.counters == nullptr) return;
+    const uint32_t t_i = warp_sum(a_rail_i), t_q = warp_sum(a_rail_q), t_both = warp_sum(a_rail_both);
     if (lane == 0) {
-        s_cnt[warp][0] = a_bit; s_cnt[warp][1] = a_rail; s_cnt[warp][2] = a_ferr; s_cnt[warp][3] = a_frames;
-        s_sum[warp][0] = a_e2; s_sum[warp][1] = a_ref2; s_sum[warp][2] = a_evm;
+        s_cnt[warp][0] = (unsigned long long)t_i + 2ull * t_q - 2ull * t_both;     // bit errors
+        s_cnt[warp][1] = (unsigned long long)t_i + t_q;                             // rail errors
+        s_cnt[warp][2] = a_ferr; s_cnt[warp][3] = a_frames;
+        s_sum[warp][0] = a_e2; s_sum[warp][1] = a_evm;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long c[4] = {0, 0, 0, 0}; double s[3] = {0, 0, 0};
+        unsigned long long c[4] = {0, 0, 0, 0}; double s[2] = {0, 0};
         for (int w = 0; w < kWarpsPerBlock; ++w) {
             for (int k = 0; k < 4; ++k) c[k] += s_cnt[w][k];
-            for (int k = 0; k < 3; ++k) s[k] += s_sum[w][k];
+            for (int k = 0; k < 2; ++k) s[k] += s_sum[w][k];
         }
         if (c[3] != 0) {
             ofdm_counters *o = p.counters;
@@ -431,8 +508,8 @@ __global__ void __launch_bounds__(kThreads) k_rx_frames(RxParams p)
             atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames), c[3]);
             atomicAdd(reinterpret_cast<unsigned long long *>(&o->bits), c[3] * 96ull * (unsigned long long)n_sym);
             atomicAdd(&o->sum_err2, s[0]);
-            atomicAdd(&o->sum_ref2, s[1]);
-            atomicAdd(&o->sum_evm_lin, s[2]);
+            atomicAdd(&o->sum_ref2, (double)c[3] * ref2_frame);
+            atomicAdd(&o->sum_evm_lin, s[1]);
         }
     }
 }
