@@ -62,6 +62,22 @@ __device__ __forceinline__ void bf_unit(float2 &e, float2 &o)
     o.x = __fsub_rn(a.x, w.x); o.y = __fsub_rn(a.y, w.y);
 }
 
+// k = sz/4: W = (6.1e-17, -1) exactly as cexp() returns it.  The product is
+// (fl64(wr*c) + d, fl64(wr*d) - c) rounded to float, which is (d, -c) unless the 2^-53.9-scaled
+// term reaches a quarter ulp of the float it is added to (|c| >= 1.2e8 |d|, or d == 0): those
+// inputs (exact zeros in noise-free frames, mostly) take the full double product.
+__device__ __forceinline__ void bf_quarter(float2 &e, float2 &o)
+{
+    const float c = o.x, d = o.y;
+    if (fabsf(c) * 1e-8f < fabsf(d) && fabsf(d) * 1e-8f < fabsf(c)) {
+        float2 a = e;
+        e.x = __fadd_rn(a.x, d); e.y = __fsub_rn(a.y, c);
+        o.x = __fsub_rn(a.x, d); o.y = __fadd_rn(a.y, c);
+    } else {
+        bf_exact(e, o, kW16r, kW16i);
+    }
+}
+
 struct TwExact { double2 w16, w32a, w32b, w64a, w64b, w64c, w64d; };
 
 __device__ __forceinline__ TwExact load_tw_exact(int t)
@@ -80,11 +96,11 @@ __device__ __forceinline__ void fft64_exact(float2 (&v)[8], const TwExact &tw, f
 {
     // sz = 2, 4, 8 inside the lane (positions 8t..8t+7)
     bf_unit(v[0], v[1]); bf_unit(v[2], v[3]); bf_unit(v[4], v[5]); bf_unit(v[6], v[7]);
-    bf_unit(v[0], v[2]); bf_exact(v[1], v[3], kW16r, kW16i);
-    bf_unit(v[4], v[6]); bf_exact(v[5], v[7], kW16r, kW16i);
+    bf_unit(v[0], v[2]); bf_quarter(v[1], v[3]);
+    bf_unit(v[4], v[6]); bf_quarter(v[5], v[7]);
     bf_unit(v[0], v[4]);
     bf_exact(v[1], v[5], kW8r, kW8i);
-    bf_exact(v[2], v[6], kW16r, kW16i);
+    bf_quarter(v[2], v[6]);
     bf_exact(v[3], v[7], kW24r, kW24i);
     // 8x8 transpose: position q = 8*rev3(u) + i  ->  lane q%8, slot q/8
     const int row = rev3(u) * 9;

@@ -282,51 +282,62 @@ __device__ __forceinline__ float2 div_fast(float2 n, float2 h)
     return make_float2(fmaf(n.x, h.x, n.y * h.y) * inv, fmaf(n.y, h.x, -n.x * h.y) * inv);
 }
 
-// One data bin through equalise :1050, slicer :860-868, demod :883-902, BER :1158 and the EVM terms :1114.
-// Returns the rail-error flags (bit0 = I rail, bit1 = Q rail).  Bit errors follow from the non-Gray map
-// (SURVEY Q5): a Q-rail error flips bit a, and bit b flips when exactly one rail is wrong.
-//
-// EXACT, no dump: the decision is the sign of the float(num/den) the reference computes.  For normal
-// magnitudes that is the sign of the exact numerator a*c+b*d (resp. b*c-a*d); the fp32 evaluation is
-// trusted only when it is at least 2^-20 of the magnitude bound m (its error is < 2^-23 m) and m, den
-// sit in [1e-15, 1e15] (no float under/overflow of the quotient); everything else takes the exact
-// double-widened division.  The EVM terms use the fp32 quotient (1e-5 contract).
-template <bool EXACT, bool DUMP>
-__device__ __forceinline__ uint32_t process_bin(float2 F, float2 Hh, uint32_t txp, float &e2, float2 &E_out, bool &re_pos, bool &im_pos)
+// One data bin through equalise :1050, slicer :860-868, demod :883-902, BER :1158 and the EVM terms :1114
+// for the dump path (every value materialised, exact division in EXACT mode).
+// Returns the rail-error flags (bit0 = I rail, bit1 = Q rail).
+template <bool EXACT>
+__device__ __forceinline__ uint32_t process_bin_full(float2 F, float2 Hh, uint32_t txp, float &e2, float2 &E, bool &re_pos, bool &im_pos)
 {
-    const float a = F.x, b = F.y, c = Hh.x, d = Hh.y;
-    float2 E;
-    if (EXACT && DUMP) {
-        E = div_exact(F, Hh);
-        re_pos = E.x > 0.f; im_pos = E.y > 0.f;
-    } else {
-        const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
-        const float den = fmaf(c, c, d * d);
-        float inv;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
-        E = make_float2(sr * inv, si * inv);
-        re_pos = sr > 0.f; im_pos = si > 0.f;
-        if (EXACT) {
-            const float m = (fabsf(a) + fabsf(b)) * (fabsf(c) + fabsf(d));
-            const float lim = 1e-6f * m;
-            const bool safe = fabsf(sr) > lim && fabsf(si) > lim && fminf(m, den) > 1e-15f && fmaxf(m, den) < 1e15f;
-            if (!safe) {
-                E = div_exact(F, Hh);
-                re_pos = E.x > 0.f; im_pos = E.y > 0.f;
-            }
-        }
-    }
+    E = EXACT ? div_exact(F, Hh) : div_fast(F, Hh);
+    re_pos = E.x > 0.f; im_pos = E.y > 0.f;
     const uint32_t A = txp & 1u, B = txp >> 1;
     const bool i_pos = (A ^ B) == 0u, q_pos = A == 0u;           // tx rails, QPSK_Modulator :423-430
     const float er = E.x - (i_pos ? kQpsk : -kQpsk), ei = E.y - (q_pos ? kQpsk : -kQpsk);
     e2 = fmaf(er, er, fmaf(ei, ei, e2));
-    E_out = E;
     return (uint32_t)(re_pos != i_pos) | ((uint32_t)(im_pos != q_pos) << 1);
 }
 
-// Fused receiver.  DUMP = false is the sweep path: totals only, bins of the two first data symbols
-// are shared with the (otherwise idle) LTS lane groups so all 32 lanes work through the decision
-// stage.  DUMP = true writes any of the per-bin / per-frame outputs and always divides exactly.
+// The sweep path's version of the same bin.  Returns the rail errors packed for cheap accumulation:
+// bits 0..7 += I-rail error, 8..15 += Q-rail error, 16..23 += both.  (Bit errors follow from the
+// non-Gray map, SURVEY Q5: a Q error flips bit a, bit b flips when exactly one rail is wrong.)
+//
+// EXACT: the decision the reference takes is the sign of float(num/den) (:1050, :860).  For normal
+// magnitudes that is the sign of the exact numerator a*c+b*d (resp. b*c-a*d).  Its fp32 evaluation
+// errs by < 2^-23 m, m = (|a|+|b|)(|c|+|d|), and is trusted only above 1e-6 m, with m in
+// [1e-20, 1e15] and den < 1e15 so that neither the products nor the float quotient can underflow;
+// every other case (about 1e-6 of the bins, plus degenerate frames) takes the exact double-widened
+// division.  The EVM term uses the fp32 quotient (1e-5 contract).
+template <bool EXACT>
+__device__ __forceinline__ uint32_t process_bin_hot(float2 F, float2 Hh, uint32_t txp, bool valid, float &e2)
+{
+    const float a = F.x, b = F.y, c = Hh.x, d = Hh.y;
+    const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
+    const float den = fmaf(c, c, d * d);
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+    float ex = sr * inv, ey = si * inv;
+    const uint32_t sq = txp << 31, sx = (txp ^ (txp >> 1)) << 31;          // IEEE sign bits of the tx Q / I rails
+    uint32_t ei_ = (__float_as_uint(sr) ^ sx) >> 31, eq_ = (__float_as_uint(si) ^ sq) >> 31;
+    if (EXACT) {
+        const float m = (fabsf(a) + fabsf(b)) * (fabsf(c) + fabsf(d));
+        const bool safe = fminf(fabsf(sr), fabsf(si)) > 1e-6f * m && m > 1e-20f && fmaxf(m, den) < 1e15f;
+        if (!safe && valid) {
+            const float2 E = div_exact(F, Hh);
+            ex = E.x; ey = E.y;
+            ei_ = (uint32_t)((E.x > 0.f) != (sx == 0u));
+            eq_ = (uint32_t)((E.y > 0.f) != (sq == 0u));
+        }
+    }
+    const float er = ex - __uint_as_float(0x3F3504F3u | sx), eim = ey - __uint_as_float(0x3F3504F3u | sq);
+    const float t = fmaf(er, er, eim * eim);
+    e2 += valid ? t : 0.f;
+    const uint32_t pk = ei_ | (eq_ << 8) | ((ei_ & eq_) << 16);
+    return valid ? pk : 0u;
+}
+
+// Fused receiver.  DUMP = false is the sweep path: totals only; the bins of the two first data
+// symbols are shared with the (otherwise idle) LTS lane groups so all 32 lanes work through the
+// decision stage.  DUMP = true writes any of the per-bin / per-frame outputs, always dividing exactly.
 template <bool EXACT, int NOISE, bool DUMP>
 __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p)
 {
@@ -338,8 +349,9 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
     const uint32_t grp_mask = 0xFFu << (grp * 8);
     float2 *tile = s_tile[warp] + grp * kGroupPitch;
+    const float2 *ltsA = s_lts[warp][0], *ltsB = s_lts[warp][1];
     Tw<EXACT> tw; tw.load(u);
-    // per-lane bin info for natural bins u + 8j, one byte each: data index, or >= 0x80 for null / pilot
+    // per-lane bin info for natural bins u + 8j: data index byte (>= 0x80: null / pilot) and the L sign
     uint32_t dlo = 0, dhi = 0, lneg = 0, lnul = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -348,106 +360,115 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
         const int l = c_tab.bin_lts[u + 8 * j];
         lneg |= (uint32_t)(l < 0) << j; lnul |= (uint32_t)(l == 0) << j;
     }
+    // H = 0.5*(A+B)*conj(L), :848; L is real so the scaling is exact in float
+    auto h_of = [&](int j) {
+        const float2 A = ltsA[u + 8 * j], B = ltsB[u + 8 * j];
+        const float sc = ((lnul >> j) & 1u) ? 0.f : (((lneg >> j) & 1u) ? -0.5f : 0.5f);
+        return make_float2(__fmul_rn(__fadd_rn(A.x, B.x), sc), __fmul_rn(__fadd_rn(A.y, B.y), sc));
+    };
     const int n_sym = p.n_sym, len = 160 + 80 * n_sym;
     const int n_pass = 1 + (n_sym > 2 ? (n_sym - 2 + 3) / 4 : 0);
     const double q = (double)kQpsk;
     const double ref2_frame = 48.0 * n_sym * (2.0 * q * q);     // sum |tx|^2 over the frame's data bins
     const float inv_ref2 = (float)(1.0 / ref2_frame);
+    const long stride = (long)gridDim.x * kWarpsPerBlock;
+    const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp;
 
-    uint32_t a_rail_i = 0, a_rail_q = 0, a_rail_both = 0, a_ferr = 0, a_frames = 0;   // per lane
-    double a_e2 = 0.0, a_evm = 0.0;                                                    // warp-uniform
+    uint32_t a_i = 0, a_q = 0, a_both = 0, a_ferr = 0, a_frames = 0;   // per lane
+    double a_e2 = 0.0, a_evm = 0.0;                                     // warp-uniform
 
-    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < p.n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
-        const float2 *x = p.in + f * len;
-        double sigma_d = 0.0; float sigma_f = 0.f;
+    for (long f_chunk = f_first; f_chunk < p.n_frames; f_chunk += 32 * stride) {
+        // lane l prepares sigma = sqrt((double)(P / snr_lin)) (:647, :651) of the chunk's l-th frame
+        double sig_mine = 0.0;
         if (NOISE != kNoiseNone) {
-            float np = __fdiv_rn(p.power[f], p.snr_lin);
-            sigma_d = __dsqrt_rn((double)np);
-            sigma_f = (float)sigma_d;
+            const long fl = f_chunk + lane * stride;
+            if (fl < p.n_frames) sig_mine = __dsqrt_rn((double)__fdiv_rn(p.power[fl], p.snr_lin));
         }
-        float2 H[8];
-        uint32_t f_i = 0, f_q = 0, f_both = 0;
-        float f_e2 = 0.f;
-        for (int pass = 0; pass < n_pass; ++pass) {
-            const int sym = pass == 0 ? grp - 2 : 2 + (pass - 1) * 4 + grp;     // < 0: LTS half
-            const bool active = sym < n_sym;
-            const int n0 = sym < 0 ? 32 + 64 * grp : 176 + 80 * sym;           // Channel_Estimation :837-838, CP strip :1028
-            float2 v[8];
-            float z[8];
-            if (NOISE == kNoisePhilox && active) {
-                int base = window_block_base(n0) + u;
-                float za[4], zb[4];
-                philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)base, kDomainNoise, za);
-                philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)(base + 8), kDomainNoise, zb);
+        float c_e2 = 0.f, c_evm = 0.f;
+        for (int k = 0; k < 32; ++k) {
+            const long f = f_chunk + k * stride;
+            if (f >= p.n_frames) break;
+            const float2 *x = p.in + f * len;
+            const double sigma_d = NOISE != kNoiseNone ? __shfl_sync(0xffffffffu, sig_mine, k) : 0.0;
+            const float sigma_f = (float)sigma_d;
+            uint32_t f_i = 0, f_q = 0, f_both = 0;
+            float f_e2 = 0.f;
+            for (int pass = 0; pass < n_pass; ++pass) {
+                const int sym = pass == 0 ? grp - 2 : 2 + (pass - 1) * 4 + grp;     // < 0: LTS half
+                const bool active = sym < n_sym;
+                const int n0 = sym < 0 ? 32 + 64 * grp : 176 + 80 * sym;           // Channel_Estimation :837-838, CP strip :1028
+                float2 v[8];
+                float z[8];
+                if (NOISE == kNoisePhilox && active) {
+                    const int base = window_block_base(n0) + u;
+                    float za[4], zb[4];
+                    philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)base, kDomainNoise, za);
+                    philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)(base + 8), kDomainNoise, zb);
 #pragma unroll
-                for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = slot_m<EXACT>(i);
-                float2 s = make_float2(0.f, 0.f);
-                if (active) {
-                    s = x[n0 + u + 8 * m];
-                    if (NOISE == kNoiseInject) s.x = add_noise<EXACT>(s.x, p.g[f * len + n0 + u + 8 * m], sigma_d, sigma_f);
-                    if (NOISE == kNoisePhilox) s.x = add_noise<EXACT>(s.x, z[m], sigma_d, sigma_f);
+                    for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
                 }
-                v[i] = s;
-            }
-            fft64<EXACT>(v, tw, tile, u);                                       // natural bins u + 8j
-            if (pass == 0) {
-                if (grp < 2) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) s_lts[warp][grp][u + 8 * j] = v[j];
+                for (int i = 0; i < 8; ++i) {
+                    const int m = slot_m<EXACT>(i);
+                    float2 s = make_float2(0.f, 0.f);
+                    if (active) {
+                        s = x[n0 + u + 8 * m];
+                        if (NOISE == kNoiseInject) s.x = add_noise<EXACT>(s.x, p.g[f * len + n0 + u + 8 * m], sigma_d, sigma_f);
+                        if (NOISE == kNoisePhilox) s.x = add_noise<EXACT>(s.x, z[m], sigma_d, sigma_f);
+                    }
+                    v[i] = s;
                 }
-                __syncwarp();
+                fft64<EXACT>(v, tw, tile, u);                                       // natural bins u + 8j
+                if (pass == 0) {
+                    if (grp < 2) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {                                   // H = 0.5*(A+B)*conj(L)  :848 (L real: exact scaling)
-                    const float2 A = s_lts[warp][0][u + 8 * j], B = s_lts[warp][1][u + 8 * j];
-                    const float sc = ((lnul >> j) & 1u) ? 0.f : (((lneg >> j) & 1u) ? -0.5f : 0.5f);
-                    H[j] = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), sc), __fmul_rn(__fadd_rn(A.y, B.y), sc));
-                }
-                if (DUMP && p.dump.H != nullptr && grp == 0) {
-                    float2 *Hout = reinterpret_cast<float2 *>(p.dump.H) + f * 64;
+                        for (int j = 0; j < 8; ++j) s_lts[warp][grp][u + 8 * j] = v[j];
+                    }
+                    __syncwarp();
+                    if (DUMP && p.dump.H != nullptr && grp == 0) {
+                        float2 *Hout = reinterpret_cast<float2 *>(p.dump.H) + f * 64;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) Hout[(u + 8 * j + 32) & 63] = H[j];
-                }
-                __syncwarp();
-            }
-            if (!DUMP && pass == 0) {
-                // lanes of LTS group g take over slots 4..7 of data group g+2 (same symbol g)
-                const int dsym = grp & 1;
-                float2 X[4], Hs[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float wx = __shfl_down_sync(0xffffffffu, v[4 + k].x, 16), wy = __shfl_down_sync(0xffffffffu, v[4 + k].y, 16);
-                    X[k] = grp < 2 ? make_float2(wx, wy) : v[k];
-                    Hs[k] = grp < 2 ? H[4 + k] : H[k];
-                }
-                const uint32_t dsel = grp < 2 ? dhi : dlo;
-                if (dsym < n_sym) {
-                    const uint32_t *w = p.tx_bits + (f * n_sym + dsym) * 3;
-                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t d = (dsel >> (8 * k)) & 0xFFu;
-                        if (d >= 0x80u) continue;
-                        float2 E; bool rp, ip;
-                        const uint32_t e = process_bin<EXACT, false>(X[k], Hs[k], bit_pair(w0, w1, w2, (int)d), f_e2, E, rp, ip);
-                        f_i += e & 1u; f_q += e >> 1; f_both += (e == 3u);
+                        for (int j = 0; j < 8; ++j) Hout[(u + 8 * j + 32) & 63] = h_of(j);
                     }
                 }
-            } else if (active && sym >= 0) {
-                const uint32_t *w = p.tx_bits + (f * n_sym + sym) * 3;
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-                uint32_t o0 = 0, o1 = 0, o2 = 0;
+                if (!DUMP && pass == 0) {
+                    // lanes of LTS group g take over slots 4..7 of data group g+2 (the same symbol g)
+                    const int dsym = grp & 1, off = grp < 2 ? 4 : 0;
+                    const uint32_t dsel = grp < 2 ? dhi : dlo;
+                    const uint32_t *w = p.tx_bits + (f * n_sym + dsym) * 3;
+                    uint32_t w0 = 0, w1 = 0, w2 = 0;
+                    if (dsym < n_sym) { w0 = w[0]; w1 = w[1]; w2 = w[2]; }
+                    uint32_t pk = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t d = ((j < 4 ? dlo : dhi) >> (8 * (j & 3))) & 0xFFu;
-                    if (d >= 0x80u) continue;                                   // demap :1063-1068 keeps the 48 data bins
-                    float2 E; bool rp, ip;
-                    const uint32_t e = process_bin<EXACT, DUMP>(v[j], H[j], bit_pair(w0, w1, w2, (int)d), f_e2, E, rp, ip);
-                    f_i += e & 1u; f_q += e >> 1; f_both += (e == 3u);
-                    if (DUMP) {
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float wx = __shfl_down_sync(0xffffffffu, v[4 + kk].x, 16), wy = __shfl_down_sync(0xffffffffu, v[4 + kk].y, 16);
+                        const float2 X = grp < 2 ? make_float2(wx, wy) : v[kk];
+                        const uint32_t d = (dsel >> (8 * kk)) & 0xFFu;
+                        pk += process_bin_hot<EXACT>(X, h_of(off + kk), bit_pair(w0, w1, w2, (int)d), d < 0x80u && dsym < n_sym, f_e2);
+                    }
+                    f_i += pk & 0xFFu; f_q += (pk >> 8) & 0xFFu; f_both += pk >> 16;
+                } else if (!DUMP) {
+                    const int ssym = active ? sym : 0;
+                    const uint32_t *w = p.tx_bits + (f * n_sym + ssym) * 3;
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                    uint32_t pk = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t d = ((j < 4 ? dlo : dhi) >> (8 * (j & 3))) & 0xFFu;
+                        pk += process_bin_hot<EXACT>(v[j], h_of(j), bit_pair(w0, w1, w2, (int)d), d < 0x80u && active, f_e2);
+                    }
+                    f_i += pk & 0xFFu; f_q += (pk >> 8) & 0xFFu; f_both += pk >> 16;
+                } else if (active && sym >= 0) {
+                    const uint32_t *w = p.tx_bits + (f * n_sym + sym) * 3;
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                    uint32_t o0 = 0, o1 = 0, o2 = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t d = ((j < 4 ? dlo : dhi) >> (8 * (j & 3))) & 0xFFu;
+                        if (d >= 0x80u) continue;                                   // demap :1063-1068 keeps the 48 data bins
+                        float2 E; bool rp, ip;
+                        const uint32_t e = process_bin_full<EXACT>(v[j], h_of(j), bit_pair(w0, w1, w2, (int)d), f_e2, E, rp, ip);
+                        f_i += e & 1u; f_q += e >> 1; f_both += (e == 3u);
                         if (p.dump.eq != nullptr) reinterpret_cast<float2 *>(p.dump.eq)[(f * n_sym + sym) * 48 + d] = E;
                         if (p.dump.sliced != nullptr)
                             reinterpret_cast<float2 *>(p.dump.sliced)[(f * n_sym + sym) * 48 + d] =
@@ -455,38 +476,39 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
                         const uint32_t sh = demod_pair(rp, ip) << (2 * (d & 15u));
                         if (d < 16u) o0 |= sh; else if (d < 32u) o1 |= sh; else o2 |= sh;
                     }
-                }
-                if (DUMP && p.dump.bits != nullptr) {
+                    if (p.dump.bits != nullptr) {
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        o0 |= __shfl_xor_sync(grp_mask, o0, o);
-                        o1 |= __shfl_xor_sync(grp_mask, o1, o);
-                        o2 |= __shfl_xor_sync(grp_mask, o2, o);
+                        for (int o = 1; o < 8; o <<= 1) {
+                            o0 |= __shfl_xor_sync(grp_mask, o0, o);
+                            o1 |= __shfl_xor_sync(grp_mask, o1, o);
+                            o2 |= __shfl_xor_sync(grp_mask, o2, o);
+                        }
+                        if (u == 0) { uint32_t *ob = p.dump.bits + (f * n_sym + sym) * 3; ob[0] = o0; ob[1] = o1; ob[2] = o2; }
                     }
-                    if (u == 0) { uint32_t *ob = p.dump.bits + (f * n_sym + sym) * 3; ob[0] = o0; ob[1] = o1; ob[2] = o2; }
+                }
+                __syncwarp();
+            }
+            // bit errors of a bin = q_err + (i_err xor q_err) = i + 2q - 2*both   (BER :1158 under the map of :423-430)
+            const uint32_t f_bit_lane = f_i + 2u * f_q - 2u * f_both;
+            const bool any_err = __any_sync(0xffffffffu, f_bit_lane != 0u);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) f_e2 += __shfl_xor_sync(0xffffffffu, f_e2, o);
+            const float evm = sqrtf(f_e2 * inv_ref2);                               // :1124
+            if (DUMP) {
+                const uint32_t f_bit = warp_sum(f_bit_lane);
+                if (lane == 0) {
+                    if (p.dump.frame_bit_errors != nullptr) p.dump.frame_bit_errors[f] = (int32_t)f_bit;
+                    if (p.dump.frame_evm_lin != nullptr) p.dump.frame_evm_lin[f] = evm;
                 }
             }
-            __syncwarp();
+            a_i += f_i; a_q += f_q; a_both += f_both;
+            a_ferr += any_err; a_frames += 1;
+            c_e2 += f_e2; c_evm += evm;
         }
-        // bit errors of a bin = q_err + (i_err xor q_err) = i + 2q - 2*both   (BER :1158 under the map of :423-430)
-        const uint32_t f_bit_lane = f_i + 2u * f_q - 2u * f_both;
-        const bool any_err = __any_sync(0xffffffffu, f_bit_lane != 0u);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) f_e2 += __shfl_xor_sync(0xffffffffu, f_e2, o);
-        const float evm = sqrtf(f_e2 * inv_ref2);                               // :1124
-        if (DUMP) {
-            const uint32_t f_bit = warp_sum(f_bit_lane);
-            if (lane == 0) {
-                if (p.dump.frame_bit_errors != nullptr) p.dump.frame_bit_errors[f] = (int32_t)f_bit;
-                if (p.dump.frame_evm_lin != nullptr) p.dump.frame_evm_lin[f] = evm;
-            }
-        }
-        a_rail_i += f_i; a_rail_q += f_q; a_rail_both += f_both;
-        a_ferr += any_err; a_frames += 1;
-        a_e2 += (double)f_e2; a_evm += (double)evm;
+        a_e2 += (double)c_e2; a_evm += (double)c_evm;
     }
     if (p.counters == nullptr) return;
-    const uint32_t t_i = warp_sum(a_rail_i), t_q = warp_sum(a_rail_q), t_both = warp_sum(a_rail_both);
+    const uint32_t t_i = warp_sum(a_i), t_q = warp_sum(a_q), t_both = warp_sum(a_both);
     if (lane == 0) {
         s_cnt[warp][0] = (unsigned long long)t_i + 2ull * t_q - 2ull * t_both;     // bit errors
         s_cnt[warp][1] = (unsigned long long)t_i + t_q;                             // rail errors
