@@ -87,6 +87,9 @@ SIGNATURES = {
     "ofdm_awgn_rx_philox": (_I, [_VP, _VP, _VP, _VP, _F, _U32, _U32, _U64, _L, _I, _I, _VP, C.POINTER(RxDump)]),
     "ofdm_sweep_inject_host": (_I, [_VP, _VP, _VP, _L, _I, _VP, _I, _I, C.POINTER(Counters)]),
     "ofdm_sweep_inject_dev": (_I, [_VP, _VP, _VP, _L, _I, _VP, _I, _I, C.POINTER(Counters)]),
+    "ofdm_random_bits": (_I, [_VP, _U32, _U64, _L, _I, _VP]),
+    "ofdm_mc_sweep_philox_dev": (_I, [_VP, _U32, _U64, _L, _I, _VP, _I, _I, _VP]),
+    "ofdm_mc_sweep_philox": (_I, [_VP, _U32, _U64, _L, _I, _VP, _I, _I, C.POINTER(Counters)]),
     "ofdm_counters_finalize": (_I, [C.POINTER(Counters), C.POINTER(_F)]),
     "ofdm_write_float_array_to_file": (_I, [_VP, _I, C.c_char_p]),
     "ofdm_write_complex_array_to_file": (_I, [_VP, _I, C.c_char_p, _I]),
@@ -310,6 +313,22 @@ class Ofdm:
         out = (Counters * len(snr))()
         self._check(self.lib.ofdm_sweep_inject_dev(self.h, _ptr(bits_packed), _ptr(g), n_frames, n_sym, snr.ctypes.data,
                                                    len(snr), mode, out))
+        return list(out)
+
+    def random_bits(self, seed, frame0, n_frames, n_sym):
+        out = self.empty((n_frames * n_sym * 3,), self.torch.int32)
+        self._check(self.lib.ofdm_random_bits(self.h, seed, frame0, n_frames, n_sym, _ptr(out)))
+        return out
+
+    def mc_sweep_philox(self, seed, frame0, n_frames, n_sym, snr_db, mode, counters=None):
+        """counters=None: returns host totals (synchronises); else accumulates into the device counters tensor."""
+        snr = np.ascontiguousarray(snr_db, dtype=np.float32)
+        if counters is not None:
+            self._check(self.lib.ofdm_mc_sweep_philox_dev(self.h, seed, frame0, n_frames, n_sym, snr.ctypes.data, len(snr), mode,
+                                                          _ptr(counters)))
+            return None
+        out = (Counters * len(snr))()
+        self._check(self.lib.ofdm_mc_sweep_philox(self.h, seed, frame0, n_frames, n_sym, snr.ctypes.data, len(snr), mode, out))
         return list(out)
 
     def finalize(self, counters):

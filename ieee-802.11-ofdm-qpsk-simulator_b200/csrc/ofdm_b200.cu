@@ -6,7 +6,7 @@
 #include <cstring>
 #include <new>
 
-#include "ofdm_kernels.cuh"
+#include "ofdm_chain.cuh"
 
 using namespace ofdm;
 
@@ -115,8 +115,20 @@ int upload_tables(ofdm_ctx *ctx, const float *lts_time /* nullable */)
         int c = (p + 32) & 63;
         t.bin_data[p] = by_c[c];
         t.bin_lts[p] = (c >= 6 && c <= 58) ? kLk[c - 6] : 0;
+        if (by_c[c] >= 0) t.data_bin[by_c[c]] = (int8_t)p;
     }
-    if (lts_time) memcpy(t.lts_time, lts_time, sizeof t.lts_time);
+    if (lts_time) {
+        memcpy(t.lts_time, lts_time, sizeof t.lts_time);
+        // OFDM.c:637-641 over the LTS slot: float accumulator, double terms cabs*cabs (libm hypot == the reference's cabs)
+        float acc = 0.0f; double sum = 0.0;
+        for (int i = 0; i < 160; ++i) {
+            double h = hypot((double)lts_time[2 * i], (double)lts_time[2 * i + 1]);
+            acc = (float)((double)acc + h * h);
+            sum += (double)lts_time[2 * i] * lts_time[2 * i] + (double)lts_time[2 * i + 1] * lts_time[2 * i + 1];
+        }
+        t.lts_power_prefix = acc;
+        t.lts_power_sum = (float)sum;
+    }
     OFDM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, ctx->stream));
     OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return OFDM_OK;
@@ -559,6 +571,77 @@ int ofdm_sweep_inject_host(ofdm_ctx *ctx, const uint32_t *bits_host, const float
     OFDM_CUDA(ctx, cudaMemcpyAsync(bits, bits_host, bits_bytes, cudaMemcpyHostToDevice, ctx->stream));
     OFDM_CUDA(ctx, cudaMemcpyAsync(g, g_host, g_bytes, cudaMemcpyHostToDevice, ctx->stream));
     return ofdm_sweep_inject_dev(ctx, (const uint32_t *)bits, (const float *)g, n_frames, n_sym, snr_db, n_snr, mode, out_host);
+}
+
+// ------------------------------------------------------------------ Philox Monte-Carlo
+int ofdm_random_bits(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, uint32_t *bits)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, bits != nullptr);
+    long n = n_frames * n_sym;
+    k_philox_bits<<<blocks_1d(n), 256, 0, ctx->stream>>>(seed, frame0, n, n_sym, bits);
+    return check_launch(ctx, "k_philox_bits");
+}
+
+int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, const float *snr_db,
+                             int n_snr, int mode, ofdm_counters *counters)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0 && n_snr <= kMaxSnr);
+    if (n_frames == 0 || n_snr == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, snr_db != nullptr && counters != nullptr);
+    if (n_sym == 2) {
+        McParams p;
+        memset(&p, 0, sizeof p);
+        p.seed = seed; p.frame0 = frame0; p.n_frames = n_frames; p.n_snr = n_snr; p.counters = counters;
+        for (int i = 0; i < n_snr; ++i) p.snr_lin[i] = snr_linear(snr_db[i]);
+        const size_t smem = mc_smem_bytes();
+        if (mode == OFDM_MODE_EXACT) {
+            OFDM_CUDA(ctx, cudaFuncSetAttribute(k_mc_philox<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = grid_for(ctx, k_mc_philox<true>, smem, kWarpsPerBlock, n_frames);
+            k_mc_philox<true><<<grid, kThreads, smem, ctx->stream>>>(p);
+        } else {
+            OFDM_CUDA(ctx, cudaFuncSetAttribute(k_mc_philox<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = grid_for(ctx, k_mc_philox<false>, smem, kWarpsPerBlock, n_frames);
+            k_mc_philox<false><<<grid, kThreads, smem, ctx->stream>>>(p);
+        }
+        return check_launch(ctx, "k_mc_philox");
+    }
+    // other frame shapes: the same streams through the staged kernels, in chunks that bound the scratch memory
+    const int len = OFDM_FRAME_LEN(n_sym);
+    const long chunk = 262144;
+    for (long f0 = 0; f0 < n_frames; f0 += chunk) {
+        const long n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        void *bits = nullptr, *frames = nullptr, *power = nullptr;
+        if (int st = ensure_scratch(ctx, 4, (size_t)n * n_sym * 3 * sizeof(uint32_t), &bits)) return st;
+        if (int st = ensure_scratch(ctx, 1, (size_t)n * len * 2 * sizeof(float), &frames)) return st;
+        if (int st = ensure_scratch(ctx, 2, (size_t)n * sizeof(float), &power)) return st;
+        if (int st = ofdm_random_bits(ctx, seed, frame0 + (uint64_t)f0, n, n_sym, (uint32_t *)bits)) return st;
+        if (int st = ofdm_tx_frames(ctx, (const uint32_t *)bits, (float *)frames, (float *)power, n, n_sym, mode)) return st;
+        for (int i = 0; i < n_snr; ++i)
+            if (int st = ofdm_awgn_rx_philox(ctx, (const float *)frames, (const float *)power, (const uint32_t *)bits, snr_db[i], seed,
+                                             (uint32_t)i, frame0 + (uint64_t)f0, n, n_sym, mode, counters + i, nullptr))
+                return st;
+    }
+    return OFDM_OK;
+}
+
+int ofdm_mc_sweep_philox(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, const float *snr_db,
+                         int n_snr, int mode, ofdm_counters *out_host)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_snr >= 0 && n_snr <= kMaxSnr && (n_snr == 0 || out_host != nullptr));
+    memset(out_host, 0, sizeof(ofdm_counters) * (size_t)n_snr);
+    if (n_snr == 0 || n_frames == 0) return OFDM_OK;
+    void *cnt = nullptr;
+    if (int st = ensure_scratch(ctx, 3, sizeof(ofdm_counters) * (size_t)n_snr, &cnt)) return st;
+    OFDM_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(ofdm_counters) * (size_t)n_snr, ctx->stream));
+    if (int st = ofdm_mc_sweep_philox_dev(ctx, seed, frame0, n_frames, n_sym, snr_db, n_snr, mode, (ofdm_counters *)cnt)) return st;
+    OFDM_CUDA(ctx, cudaMemcpyAsync(out_host, cnt, sizeof(ofdm_counters) * (size_t)n_snr, cudaMemcpyDeviceToHost, ctx->stream));
+    OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OFDM_OK;
 }
 
 int ofdm_counters_finalize(const ofdm_counters *c, float res[3])

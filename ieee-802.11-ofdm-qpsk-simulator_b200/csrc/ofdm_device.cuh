@@ -35,8 +35,10 @@ struct Tables {
     float2 tw64f[64];       // fp32 twiddles W_64^k, k = 0..63
     int8_t bin_data[64];    // natural bin p -> data index 0..47, -1 null, -2 pilot +1, -3 pilot -1
     int8_t bin_lts[64];     // natural bin p -> L value (+1, -1, 0)   OFDM.c:494
+    int8_t data_bin[48];    // data index -> natural bin p (inverse of bin_data)
     float2 lts_time[160];   // LTS slot in time (filled by the exact ifft at context creation)
-    float lts_power_prefix; // exact-mode running power sum after the 160 LTS samples (OFDM.c:637-641)
+    float lts_power_prefix; // exact-mode running float power sum after the 160 LTS samples (OFDM.c:637-641)
+    float lts_power_sum;    // sum |lts|^2 over the 160 LTS samples (fast mode)
 };
 __constant__ Tables c_tab;
 

@@ -157,6 +157,19 @@ int ofdm_sweep_inject_host(ofdm_ctx *ctx, const uint32_t *bits_host, const float
 int ofdm_sweep_inject_dev(ofdm_ctx *ctx, const uint32_t *bits_dev, const float *g_dev, long n_frames, int n_sym,
                           const float *snr_db, int n_snr, int mode, ofdm_counters *out_host);
 
+/* ---- on-chip Monte-Carlo (no reference counterpart: the reference draws from libc rand(), OFDM.c:626) ----
+ * Counter-based streams, Philox4x32-10: key (seed, stream), counter (frame_lo, frame_hi, block, domain);
+ * payload bits: domain 1, block = symbol index, words 0..2; noise: domain 0, stream = index of the SNR point,
+ * block layout in DESIGN.md.  Results depend only on (seed, frame0 + frame index), never on the GPU count. */
+int ofdm_random_bits(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, uint32_t *bits_dev);
+/* Whole sweep fused in one kernel for n_sym == 2 (bits, TX, channel, RX, counters; nothing else touches HBM);
+ * other n_sym run the same streams through the staged kernels.  n_snr <= 64.  _dev accumulates into device
+ * counters [n_snr] without synchronising (for a following NCCL all-reduce); the other returns host totals. */
+int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym,
+                             const float *snr_db, int n_snr, int mode, ofdm_counters *counters_dev);
+int ofdm_mc_sweep_philox(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym,
+                         const float *snr_db, int n_snr, int mode, ofdm_counters *out_host);
+
 /* Res[3] = {EVM_dB, EVM_AGC_dB, BER} of OFDM.c:1163-1165 from batch totals */
 int ofdm_counters_finalize(const ofdm_counters *c, float res[3]);
 

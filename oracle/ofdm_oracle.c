@@ -338,17 +338,16 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 enum { DOMAIN_NOISE = 0, DOMAIN_BITS = 1, DOMAIN_TAPS = 2 };
 
-/* payload bits: block b of a frame yields 128 bits (words r0..r3, LSB first); stream id 0 */
+/* payload bits: symbol s of a frame takes words r0..r2 (96 bits, LSB first) of block s; stream id 0 */
 void orc_philox_bits(uint32_t seed, uint64_t frame0, long n_frames, int n_sym, uint8_t *bits)
 {
-    int nbits = 96 * n_sym;
     for (long f = 0; f < n_frames; ++f) {
         uint64_t fr = frame0 + (uint64_t)f;
-        for (int blk = 0; blk * 128 < nbits; ++blk) {
-            uint32_t ctr[4] = {(uint32_t)fr, (uint32_t)(fr >> 32), (uint32_t)blk, DOMAIN_BITS}, key[2] = {seed, 0u}, r[4];
+        for (int s = 0; s < n_sym; ++s) {
+            uint32_t ctr[4] = {(uint32_t)fr, (uint32_t)(fr >> 32), (uint32_t)s, DOMAIN_BITS}, key[2] = {seed, 0u}, r[4];
             orc_philox4x32_10(ctr, key, r);
-            for (int j = 0; j < 128 && blk * 128 + j < nbits; ++j)
-                bits[f * nbits + blk * 128 + j] = (uint8_t)((r[j >> 5] >> (j & 31)) & 1u);
+            for (int j = 0; j < 96; ++j)
+                bits[(f * n_sym + s) * 96 + j] = (uint8_t)((r[j >> 5] >> (j & 31)) & 1u);
         }
     }
 }
