@@ -7,3 +7,4 @@ identifier, so load it with ``__graft_entry__.load_pkg()`` (importlib, module na
 """
 from .binding import *          # noqa: F401,F403
 from . import binding           # noqa: F401
+from . import sweep             # noqa: F401

@@ -45,9 +45,9 @@ __device__ __forceinline__ ItemConst make_items(int lane)
 // One data bin (see process_bin_hot in ofdm_kernels.cuh for the exactness argument): returns the
 // rail errors packed as  I | Q << 8 | both << 16  and adds |E - tx|^2 to e2.
 template <bool EXACT>
-__device__ __forceinline__ uint32_t item_eval(float2 F, float2 Hh, uint32_t txp, float &e2)
+__device__ __forceinline__ uint32_t item_eval(float2 F, float2 Hh, float sc, uint32_t txp, float &e2)
 {
-    return process_bin_hot<EXACT>(F, Hh, txp, true, e2);
+    return process_bin_hot<EXACT>(F, Hh, sc, txp, true, e2);
 }
 
 struct McParams {
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                     const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));
                     const int wsel = ic.word[t];
                     const uint32_t w = wsel == 0 ? b0.x : wsel == 1 ? b0.y : wsel == 2 ? b0.z : wsel == 3 ? b1.x : wsel == 4 ? b1.y : b1.z;
-                    pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, w >> ic.shift[t], e2);
+                    pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], w >> ic.shift[t], e2);
                 }
                 __syncwarp();
 #pragma unroll

@@ -264,14 +264,21 @@ struct RxParams {
 
 // libgcc __divsc3 as gcc 13 builds it: quotient formula in double, one rounding to float, plus its
 // zero-denominator recovery.  OFDM.c:1050
-__device__ __forceinline__ float2 div_exact(float2 n, float2 h)
+//
+// sc is the 0.5*L factor the estimate was scaled with.  The kernels form H as (A+B)*sc, which equals the
+// reference's 0.5*(A+B)*conj(L) (:848) in value but not in the sign of a zero; the recovery branch looks at
+// the sign of a zero real part, so it is rebuilt there: with hr = 0.5*(A.x+B.x), hi = 0.5*(A.y+B.y), L = (lr, -0)
+// the reference computes hr*lr - hi*(-0) = (hr*lr) + (hi*0), which is -0 only when both terms are -0.
+__device__ __forceinline__ float2 div_exact(float2 n, float2 h, float sc)
 {
     double a = n.x, b = n.y, c = h.x, d = h.y;
     double den = __dadd_rn(__dmul_rn(c, c), __dmul_rn(d, d));
     double x = __ddiv_rn(__dadd_rn(__dmul_rn(a, c), __dmul_rn(b, d)), den);
     double y = __ddiv_rn(__dsub_rn(__dmul_rn(b, c), __dmul_rn(a, d)), den);
     if (isnan(x) && isnan(y) && den == 0.0 && (!isnan(a) || !isnan(b))) {
-        double inf = copysign((double)INFINITY, c);
+        const bool lneg = sc < 0.f;
+        const bool c_neg = signbit(h.x) && (signbit(h.y) != lneg);
+        double inf = c_neg ? -(double)INFINITY : (double)INFINITY;
         x = __dmul_rn(inf, a); y = __dmul_rn(inf, b);
     }
     return make_float2(__double2float_rn(x), __double2float_rn(y));
@@ -286,9 +293,9 @@ __device__ __forceinline__ float2 div_fast(float2 n, float2 h)
 // for the dump path (every value materialised, exact division in EXACT mode).
 // Returns the rail-error flags (bit0 = I rail, bit1 = Q rail).
 template <bool EXACT>
-__device__ __forceinline__ uint32_t process_bin_full(float2 F, float2 Hh, uint32_t txp, float &e2, float2 &E, bool &re_pos, bool &im_pos)
+__device__ __forceinline__ uint32_t process_bin_full(float2 F, float2 Hh, float sc, uint32_t txp, float &e2, float2 &E, bool &re_pos, bool &im_pos)
 {
-    E = EXACT ? div_exact(F, Hh) : div_fast(F, Hh);
+    E = EXACT ? div_exact(F, Hh, sc) : div_fast(F, Hh);
     re_pos = E.x > 0.f; im_pos = E.y > 0.f;
     const uint32_t A = txp & 1u, B = txp >> 1;
     const bool i_pos = (A ^ B) == 0u, q_pos = A == 0u;           // tx rails, QPSK_Modulator :423-430
@@ -308,7 +315,7 @@ __device__ __forceinline__ uint32_t process_bin_full(float2 F, float2 Hh, uint32
 // every other case (about 1e-6 of the bins, plus degenerate frames) takes the exact double-widened
 // division.  The EVM term uses the fp32 quotient (1e-5 contract).
 template <bool EXACT>
-__device__ __forceinline__ uint32_t process_bin_hot(float2 F, float2 Hh, uint32_t txp, bool valid, float &e2)
+__device__ __forceinline__ uint32_t process_bin_hot(float2 F, float2 Hh, float sc, uint32_t txp, bool valid, float &e2)
 {
     const float a = F.x, b = F.y, c = Hh.x, d = Hh.y;
     const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
@@ -322,7 +329,7 @@ __device__ __forceinline__ uint32_t process_bin_hot(float2 F, float2 Hh, uint32_
         const float m = (fabsf(a) + fabsf(b)) * (fabsf(c) + fabsf(d));
         const bool safe = fminf(fabsf(sr), fabsf(si)) > 1e-6f * m && m > 1e-20f && fmaxf(m, den) < 1e15f;
         if (!safe && valid) {
-            const float2 E = div_exact(F, Hh);
+            const float2 E = div_exact(F, Hh, sc);
             ex = E.x; ey = E.y;
             ei_ = (uint32_t)((E.x > 0.f) != (sx == 0u));
             eq_ = (uint32_t)((E.y > 0.f) != (sq == 0u));
@@ -366,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
         const float sc = ((lnul >> j) & 1u) ? 0.f : (((lneg >> j) & 1u) ? -0.5f : 0.5f);
         return make_float2(__fmul_rn(__fadd_rn(A.x, B.x), sc), __fmul_rn(__fadd_rn(A.y, B.y), sc));
     };
+    auto sc_of = [&](int j) { return ((lnul >> j) & 1u) ? 0.f : (((lneg >> j) & 1u) ? -0.5f : 0.5f); };
     const int n_sym = p.n_sym, len = 160 + 80 * n_sym;
     const int n_pass = 1 + (n_sym > 2 ? (n_sym - 2 + 3) / 4 : 0);
     const double q = (double)kQpsk;
@@ -444,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
                         const float wx = __shfl_down_sync(0xffffffffu, v[4 + kk].x, 16), wy = __shfl_down_sync(0xffffffffu, v[4 + kk].y, 16);
                         const float2 X = grp < 2 ? make_float2(wx, wy) : v[kk];
                         const uint32_t d = (dsel >> (8 * kk)) & 0xFFu;
-                        pk += process_bin_hot<EXACT>(X, h_of(off + kk), bit_pair(w0, w1, w2, (int)d), d < 0x80u && dsym < n_sym, f_e2);
+                        pk += process_bin_hot<EXACT>(X, h_of(off + kk), sc_of(off + kk), bit_pair(w0, w1, w2, (int)d), d < 0x80u && dsym < n_sym, f_e2);
                     }
                     f_i += pk & 0xFFu; f_q += (pk >> 8) & 0xFFu; f_both += pk >> 16;
                 } else if (!DUMP) {
@@ -455,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t d = ((j < 4 ? dlo : dhi) >> (8 * (j & 3))) & 0xFFu;
-                        pk += process_bin_hot<EXACT>(v[j], h_of(j), bit_pair(w0, w1, w2, (int)d), d < 0x80u && active, f_e2);
+                        pk += process_bin_hot<EXACT>(v[j], h_of(j), sc_of(j), bit_pair(w0, w1, w2, (int)d), d < 0x80u && active, f_e2);
                     }
                     f_i += pk & 0xFFu; f_q += (pk >> 8) & 0xFFu; f_both += pk >> 16;
                 } else if (active && sym >= 0) {
@@ -467,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
                         const uint32_t d = ((j < 4 ? dlo : dhi) >> (8 * (j & 3))) & 0xFFu;
                         if (d >= 0x80u) continue;                                   // demap :1063-1068 keeps the 48 data bins
                         float2 E; bool rp, ip;
-                        const uint32_t e = process_bin_full<EXACT>(v[j], h_of(j), bit_pair(w0, w1, w2, (int)d), f_e2, E, rp, ip);
+                        const uint32_t e = process_bin_full<EXACT>(v[j], h_of(j), sc_of(j), bit_pair(w0, w1, w2, (int)d), f_e2, E, rp, ip);
                         f_i += e & 1u; f_q += e >> 1; f_both += (e == 3u);
                         if (p.dump.eq != nullptr) reinterpret_cast<float2 *>(p.dump.eq)[(f * n_sym + sym) * 48 + d] = E;
                         if (p.dump.sliced != nullptr)

@@ -1,2 +1,165 @@
-/* placeholder replaced below */
-int main(void) { return 0; }
+/*
+ * ofdm_main.c -- C host driver over the C-ABI (include/ofdm_b200.h): the batched counterpart of the
+ * reference's main() (OFDM.c:1187-1236).  Same sweep (default 35 points, 6..40 dB, OFDM.c:18,1197), same
+ * four result files in the same format (write_float_array_to_file, OFDM.c:123-143, 1228-1231) so that
+ * scripts/OFDM_Plotting.py of the reference reads them unchanged:
+ *     <outdir>/Output_SNR.txt          SNR points
+ *     <outdir>/Output_EVM_AGC.txt      EVM *before* the slicer, dB   (the reference's naming, OFDM.c:1229)
+ *     <outdir>/Output_EVM_AGC_DB.txt   EVM after the slicer, dB      (OFDM.c:1230)
+ *     <outdir>/Output_BER.txt          BER
+ * Two payload sources:
+ *   --message TEXT (default "Hey! I am Vivaswan", OFDM.c:20): Data_Generator's codec (OFDM.c:435-465,
+ *       MSB-first ASCII bits, space-padded to a multiple of 96 bits), one frame, prints the received
+ *       message per SNR point like Receiver() does (OFDM.c:1169-1182);
+ *   --frames N (N > 1): N frames of Philox random bits per SNR point through the fused Monte-Carlo kernel.
+ * There is no CPU fallback: without a CUDA device the program exits with an error.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ofdm_b200.h"
+
+#define CHECK(call)                                                                                  \
+    do {                                                                                             \
+        int st_ = (call);                                                                            \
+        if (st_ != OFDM_OK) {                                                                        \
+            fprintf(stderr, "%s failed: %s (%s)\n", #call, ofdm_strerror(st_), ctx ? ofdm_last_error(ctx) : ""); \
+            return 1;                                                                                \
+        }                                                                                            \
+    } while (0)
+
+/* Data_Generator + Decimal_To_Binary, OFDM.c:401-465: 8 bits per character, MSB first, padded with ' ' */
+static int encode_message(const char *msg, uint8_t **bits_out, int *n_sym_out)
+{
+    int len = (int)strlen(msg);
+    int n_sym = (int)ceil(8 * len / 96.0);
+    if (n_sym < 1) n_sym = 1;
+    int total_bits = n_sym * 96, total_chars = total_bits / 8;
+    uint8_t *bits = (uint8_t *)calloc((size_t)total_bits, 1);
+    if (!bits) return OFDM_ERR_NOMEM;
+    for (int i = 0; i < total_chars; ++i) {
+        int ch = i < len ? (unsigned char)msg[i] : ' ';
+        for (int j = 0; j < 8; ++j) bits[8 * i + j] = (uint8_t)((ch >> (7 - j)) & 1);
+    }
+    *bits_out = bits; *n_sym_out = n_sym;
+    return OFDM_OK;
+}
+
+static void pack_bits(const uint8_t *bits, int n_bits, uint32_t *words)
+{
+    memset(words, 0, (size_t)(n_bits / 32) * sizeof(uint32_t));
+    for (int j = 0; j < n_bits; ++j) words[j >> 5] |= (uint32_t)(bits[j] & 1u) << (j & 31);
+}
+
+/* Message_Generator + Binary_To_Decimal, OFDM.c:910-939 */
+static void decode_message(const uint32_t *words, int n_bits, char *out)
+{
+    for (int i = 0; i < n_bits / 8; ++i) {
+        int v = 0;
+        for (int j = 0; j < 8; ++j) { int b = 8 * i + j; v = v * 2 + (int)((words[b >> 5] >> (b & 31)) & 1u); }
+        out[i] = (char)v;
+    }
+    out[n_bits / 8] = 0;
+}
+
+int main(int argc, char **argv)
+{
+    const char *message = "Hey! I am Vivaswan";          /* OFDM.c:20 */
+    const char *outdir = "data", *dump = NULL;
+    long frames = 1;
+    int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0;
+    float snr_start = 6.0f, snr_step = 1.0f;             /* OFDM.c:18, :1195-1198 */
+    unsigned seed = 1;
+    for (int i = 1; i < argc; ++i) {
+        const char *a = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
+        if (!strcmp(a, "--quiet")) { quiet = 1; continue; }
+        if (!v) { fprintf(stderr, "missing value for %s\n", a); return 2; }
+        if (!strcmp(a, "--message")) message = v;
+        else if (!strcmp(a, "--frames")) frames = atol(v);
+        else if (!strcmp(a, "--nsym")) n_sym = atoi(v);
+        else if (!strcmp(a, "--snr-start")) snr_start = (float)atof(v);
+        else if (!strcmp(a, "--snr-step")) snr_step = (float)atof(v);
+        else if (!strcmp(a, "--snr-count")) n_snr = atoi(v);
+        else if (!strcmp(a, "--seed")) seed = (unsigned)strtoul(v, NULL, 10);
+        else if (!strcmp(a, "--device")) device = atoi(v);
+        else if (!strcmp(a, "--outdir")) outdir = v;
+        else if (!strcmp(a, "--dump")) dump = v;
+        else if (!strcmp(a, "--mode")) mode = !strcmp(v, "fast") ? OFDM_MODE_FAST : OFDM_MODE_EXACT;
+        else { fprintf(stderr, "unknown option %s\n", a); return 2; }
+        ++i;
+    }
+    if (n_snr < 1 || n_snr > 64 || frames < 1) { fprintf(stderr, "need 1 <= snr-count <= 64 and frames >= 1\n"); return 2; }
+
+    ofdm_ctx *ctx = NULL;
+    CHECK(ofdm_ctx_create(&ctx, device));
+
+    float SNR[64], EVM_dB[64], EVM_AGC_dB[64], BER[64];
+    for (int i = 0; i < n_snr; ++i) SNR[i] = snr_start + snr_step * (float)i;
+    ofdm_counters totals[64];
+
+    if (frames > 1) {
+        CHECK(ofdm_mc_sweep_philox(ctx, seed, 0, frames, n_sym, SNR, n_snr, mode, totals));
+    } else {
+        uint8_t *bits = NULL;
+        CHECK(encode_message(message, &bits, &n_sym));
+        const int n_bits = 96 * n_sym, n_words = 3 * n_sym, len = OFDM_FRAME_LEN(n_sym);
+        uint32_t *words = (uint32_t *)malloc((size_t)n_words * sizeof(uint32_t));
+        uint32_t *rx_words = (uint32_t *)malloc((size_t)n_words * sizeof(uint32_t));
+        char *text = (char *)malloc((size_t)n_bits / 8 + 1);
+        if (!words || !rx_words || !text) return 1;
+        pack_bits(bits, n_bits, words);
+        void *d_bits = NULL, *d_frame = NULL, *d_power = NULL, *d_cnt = NULL, *d_rx = NULL;
+        CHECK(ofdm_dev_alloc(ctx, &d_bits, (size_t)n_words * 4));
+        CHECK(ofdm_dev_alloc(ctx, &d_rx, (size_t)n_words * 4));
+        CHECK(ofdm_dev_alloc(ctx, &d_frame, (size_t)len * 8));
+        CHECK(ofdm_dev_alloc(ctx, &d_power, 4));
+        CHECK(ofdm_dev_alloc(ctx, &d_cnt, sizeof(ofdm_counters)));
+        CHECK(ofdm_memcpy_h2d(ctx, d_bits, words, (size_t)n_words * 4));
+        CHECK(ofdm_tx_frames(ctx, (const uint32_t *)d_bits, (float *)d_frame, (float *)d_power, 1, n_sym, mode));   /* Transmitter() once, :1191 */
+        if (dump) {
+            float *iq = (float *)malloc((size_t)len * 8);
+            char path[1024];
+            CHECK(ofdm_memcpy_d2h(ctx, iq, d_frame, (size_t)len * 8));
+            CHECK(ofdm_ctx_sync(ctx));
+            snprintf(path, sizeof path, "%s_real.txt", dump);     CHECK(ofdm_write_complex_array_to_file(iq, len, path, 0));
+            snprintf(path, sizeof path, "%s_complex.txt", dump);  CHECK(ofdm_write_complex_array_to_file(iq, len, path, 1));
+            free(iq);
+        }
+        for (int i = 0; i < n_snr; ++i) {                  /* SNR loop :1202-1222 */
+            ofdm_rx_dump d;
+            memset(&d, 0, sizeof d);
+            d.bits = (uint32_t *)d_rx;
+            CHECK(ofdm_memset_dev(ctx, d_cnt, 0, sizeof(ofdm_counters)));
+            CHECK(ofdm_awgn_rx_philox(ctx, (const float *)d_frame, (const float *)d_power, (const uint32_t *)d_bits, SNR[i], seed,
+                                      (uint32_t)i, 0, 1, n_sym, mode, (ofdm_counters *)d_cnt, &d));
+            CHECK(ofdm_memcpy_d2h(ctx, &totals[i], d_cnt, sizeof(ofdm_counters)));
+            CHECK(ofdm_memcpy_d2h(ctx, rx_words, d_rx, (size_t)n_words * 4));
+            CHECK(ofdm_ctx_sync(ctx));
+            if (!quiet) {
+                decode_message(rx_words, n_bits, text);
+                printf("\n\nFor SNR = %lf \n\nReceived Message: \n%s\n", SNR[i], text);      /* :1204, :1177-1182 */
+            }
+        }
+        ofdm_dev_free(ctx, d_bits); ofdm_dev_free(ctx, d_rx); ofdm_dev_free(ctx, d_frame);
+        ofdm_dev_free(ctx, d_power); ofdm_dev_free(ctx, d_cnt);
+        free(bits); free(words); free(rx_words); free(text);
+    }
+
+    for (int i = 0; i < n_snr; ++i) {
+        float Res[3];                                      /* EVM_dB, EVM_AGC_DB, BER  :1210 */
+        CHECK(ofdm_counters_finalize(&totals[i], Res));
+        EVM_dB[i] = Res[0]; EVM_AGC_dB[i] = Res[1]; BER[i] = Res[2];
+        if (!quiet) printf("\nSNR %5.1f dB  EVM dB = %lf  EVM_AGC dB = %lf  BER = %le  (%llu frames)", SNR[i], Res[0], Res[1], Res[2],
+                           (unsigned long long)totals[i].frames);
+    }
+    char path[1024];
+    snprintf(path, sizeof path, "%s/Output_SNR.txt", outdir);         CHECK(ofdm_write_float_array_to_file(SNR, n_snr, path));
+    snprintf(path, sizeof path, "%s/Output_EVM_AGC.txt", outdir);     CHECK(ofdm_write_float_array_to_file(EVM_dB, n_snr, path));
+    snprintf(path, sizeof path, "%s/Output_EVM_AGC_DB.txt", outdir);  CHECK(ofdm_write_float_array_to_file(EVM_AGC_dB, n_snr, path));
+    snprintf(path, sizeof path, "%s/Output_BER.txt", outdir);         CHECK(ofdm_write_float_array_to_file(BER, n_snr, path));
+    if (!quiet) printf("\nCode Run Successful!\n");
+    ofdm_ctx_destroy(ctx);
+    return 0;
+}
