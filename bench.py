@@ -10,7 +10,7 @@ TX, the channel and RX at one SNR point: symbols/step = frames x n_sym x n_snr.
   value   inputs resident in HBM, CUDA-event timed on the launching stream
   e2e     the same sweep through ofdm_sweep_inject_host: HOST (pinned) bits + draws, H2D copies,
           kernels and the D2H of the counters inside the timed region
-  roofline  dominant kernel k_rx_frames<exact,inject>: algorithmic bytes (3100 B per frame and SNR
+  roofline  dominant kernel k_stream_rx2<exact,inject>: algorithmic bytes (3100 B per frame and SNR
             point) / mean launch time (CUDA events around each launch in the timed region)
   cpu_baseline  the compiled reference (oracle/_ref) stage chain on a bounded sample, one thread
 
@@ -290,7 +290,7 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("k_rx_frames_exact_inject_bytes_per_launch")
+                traffic = json.load(f).get("k_stream_rx2_exact_inject_bytes_per_launch")
         ber = [c.bit_errors / max(1, c.bits) for c in resident_counts]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -303,7 +303,7 @@ def run_gpu(args):
                         "h2d_bytes_per_step": int(bits_h.numel() * 4 + g_h.numel() * 4),
                         "d2h_bytes_per_step": int(n_snr * pkg.COUNTERS_BYTES)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_rx_frames<exact,inject>", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "k_stream_rx2<exact,inject>", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "bytes_per_launch": BYTES_PER_FRAME_PASS * n_frames, "kernel_ms": k_ms,
                              "kernel_share_of_step": k_ms * n_snr / ms_step},

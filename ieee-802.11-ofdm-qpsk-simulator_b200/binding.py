@@ -61,6 +61,7 @@ SIGNATURES = {
     "ofdm_ctx_set_stream": (_I, [_VP, _VP]),
     "ofdm_ctx_stream": (_VP, [_VP]),
     "ofdm_ctx_sync": (_I, [_VP]),
+    "ofdm_ctx_set_option": (_I, [_VP, C.c_char_p, _I]),
     "ofdm_ctx_sm_count": (_I, [_VP]),
     "ofdm_ctx_launch_count": (_U64, [_VP]),
     "ofdm_dev_alloc": (_I, [_VP, C.POINTER(_VP), _SZ]),
@@ -141,6 +142,9 @@ class Ofdm:
 
     def use_stream(self, stream):
         self._check(self.lib.ofdm_ctx_set_stream(self.h, _VP(stream.cuda_stream)))
+
+    def set_option(self, name, value):
+        self._check(self.lib.ofdm_ctx_set_option(self.h, name.encode(), int(value)))
 
     def sync(self):
         self._check(self.lib.ofdm_ctx_sync(self.h))

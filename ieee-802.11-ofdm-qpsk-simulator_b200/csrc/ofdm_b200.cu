@@ -16,6 +16,7 @@ struct ofdm_ctx {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     uint64_t launches = 0;
+    bool force_generic = false;      // testing knob: route n_sym == 2 sweeps through the generic kernel too
     char err[256] = {0};
     float lts_freq[128];
     float lts_time[320];
@@ -158,10 +159,33 @@ int launch_rx_d(ofdm_ctx *ctx, bool dump, const RxParams &p)
     return dump ? launch_rx<EXACT, NOISE, true>(ctx, p) : launch_rx<EXACT, NOISE, false>(ctx, p);
 }
 
+template <bool EXACT, int NOISE>
+int launch_stream(ofdm_ctx *ctx, const RxParams &p)
+{
+    auto k = k_stream_rx2<EXACT, NOISE>;
+    const size_t smem = stream_smem_bytes();
+    OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
+    k<<<grid, kThreads, smem, ctx->stream>>>(p);
+    return check_launch(ctx, "k_stream_rx2");
+}
+
 int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
 {
     const ofdm_rx_dump &d = p.dump;
     const bool dump = d.H || d.eq || d.sliced || d.bits || d.frame_bit_errors || d.frame_evm_lin;
+    // default frame shape without per-bin outputs: the TMA-staged streaming kernel (bulk copies need 16-byte alignment)
+    const bool aligned = ((uintptr_t)p.in % 16 == 0) && (noise != kNoiseInject || (uintptr_t)p.g % 16 == 0);
+    if (!dump && p.n_sym == 2 && aligned && !ctx->force_generic) {
+        if (mode == OFDM_MODE_EXACT) {
+            if (noise == kNoiseNone) return launch_stream<true, kNoiseNone>(ctx, p);
+            if (noise == kNoiseInject) return launch_stream<true, kNoiseInject>(ctx, p);
+            return launch_stream<true, kNoisePhilox>(ctx, p);
+        }
+        if (noise == kNoiseNone) return launch_stream<false, kNoiseNone>(ctx, p);
+        if (noise == kNoiseInject) return launch_stream<false, kNoiseInject>(ctx, p);
+        return launch_stream<false, kNoisePhilox>(ctx, p);
+    }
     if (mode == OFDM_MODE_EXACT) {
         if (noise == kNoiseNone) return launch_rx_d<true, kNoiseNone>(ctx, dump, p);
         if (noise == kNoiseInject) return launch_rx_d<true, kNoiseInject>(ctx, dump, p);
@@ -280,6 +304,12 @@ int ofdm_ctx_sync(ofdm_ctx *ctx)
     if (int st = bind(ctx)) return st;
     OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return OFDM_OK;
+}
+int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value)
+{
+    if (!ctx || !name) return OFDM_ERR_INVALID;
+    if (!strcmp(name, "force_generic_rx")) { ctx->force_generic = value != 0; return OFDM_OK; }
+    return fail(ctx, OFDM_ERR_INVALID, "unknown option");
 }
 int ofdm_ctx_sm_count(const ofdm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t ofdm_ctx_launch_count(const ofdm_ctx *ctx) { return ctx ? ctx->launches : 0; }

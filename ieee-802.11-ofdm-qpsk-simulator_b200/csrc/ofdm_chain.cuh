@@ -71,7 +71,7 @@ struct WarpShared {
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    extern __shared__ __align__(128) unsigned char s_raw[];
     WarpShared *ws_all = reinterpret_cast<WarpShared *>(s_raw);
     float2 *s_ltsx = reinterpret_cast<float2 *>(s_raw + sizeof(WarpShared) * kWarpsPerBlock);   // [2][kWin] LTS halves, time
     double *s_terms = reinterpret_cast<double *>(s_ltsx + 2 * kWin);                            // [warps][160] (EXACT power)
@@ -236,5 +236,200 @@ __global__ void k_philox_bits(uint32_t seed, uint64_t frame0, long n_symbols, in
     const uint4 r = Philox::run(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), s, kDomainBits), seed, 0u);
     bits[t * 3] = r.x; bits[t * 3 + 1] = r.y; bits[t * 3 + 2] = r.z;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// k_stream_rx2 -- channel + receiver for HBM-resident frames (n_sym = 2), TMA-staged.
+//
+// Each warp streams its frames through a private ring of shared-memory stages.  One lane issues bulk
+// async copies (cp.async.bulk, the TMA engine's 1-D mode; SASS UBLKCP) for exactly the samples the receiver
+// uses -- the two LTS halves and the two symbol bodies of the IQ frame and, for injected noise, of the draw
+// buffer -- straight into bank-skewed windows, and arms an mbarrier with the byte count; the warp waits
+// on the barrier's phase, pulls its samples into registers, and immediately re-arms the stage for the frame
+// two iterations ahead, so HBM latency is covered by a full frame of transform work without holding
+// any prefetch registers.
+namespace tma {
+__device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(saddr(bar)), "r"(phase) : "memory");
+}
+}  // namespace tma
+
+constexpr int kStages = 2;
+
+struct StreamStage {
+    float2 x[4][kWin];              // LTS1, LTS2, sym0 body, sym1 body (skewed windows)
+    float g[4][kWin];               // the matching draws (injected noise only)
+};
+struct StreamWarp {
+    float2 tile[kWarpTile];
+    float2 lts[2][kWin];
+    StreamStage st[kStages];
+    uint64_t bar[kStages];
+};
+
+template <bool EXACT, int NOISE>
+__global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
+    __shared__ double s_sum[kWarpsPerBlock][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    StreamWarp &ws = reinterpret_cast<StreamWarp *>(s_raw)[warp];
+    float2 *tile = ws.tile + grp * kGroupPitch;
+    Tw<EXACT> tw; tw.load(u);
+    const ItemConst ic = make_items(lane);
+    constexpr int len = 320;
+    const long stride = (long)gridDim.x * kWarpsPerBlock;
+    const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp;
+    const double q = (double)kQpsk;
+    const double ref2_frame = 96.0 * (2.0 * q * q);
+    const float inv_ref2 = (float)(1.0 / ref2_frame);
+    constexpr uint32_t kBytes = 4 * 512 + (NOISE == kNoiseInject ? 4 * 256 : 0);
+
+    auto issue = [&](long f, int s) {          // lane 0 only
+        const float2 *x = p.in + f * len;
+        tma::expect_tx(&ws.bar[s], kBytes);
+        tma::bulk_g2s(ws.st[s].x[0], x + 32, 512, &ws.bar[s]);           // Channel_Estimation :837
+        tma::bulk_g2s(ws.st[s].x[1], x + 96, 512, &ws.bar[s]);           //                    :838
+        tma::bulk_g2s(ws.st[s].x[2], x + 176, 512, &ws.bar[s]);          // CP strip :1028 (symbol 0)
+        tma::bulk_g2s(ws.st[s].x[3], x + 256, 512, &ws.bar[s]);          //                (symbol 1)
+        if (NOISE == kNoiseInject) {
+            const float *g = p.g + f * len;
+            tma::bulk_g2s(ws.st[s].g[0], g + 32, 256, &ws.bar[s]);
+            tma::bulk_g2s(ws.st[s].g[1], g + 96, 256, &ws.bar[s]);
+            tma::bulk_g2s(ws.st[s].g[2], g + 176, 256, &ws.bar[s]);
+            tma::bulk_g2s(ws.st[s].g[3], g + 256, 256, &ws.bar[s]);
+        }
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) tma::mbar_init(&ws.bar[s], 1);
+        tma::fence_mbar_init();
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int s = 0; s < kStages; ++s)
+            if (f_first + s * stride < p.n_frames) issue(f_first + s * stride, s);
+
+    uint32_t a_i = 0, a_q = 0, a_both = 0, a_ferr = 0, a_frames = 0;
+    double a_e2 = 0.0, a_evm = 0.0;
+    const int blk_base = (grp < 2 ? 8 + 16 * grp : 44 + 20 * (grp - 2)) + u;
+    long k = 0;
+    for (long f_chunk = f_first; f_chunk < p.n_frames; f_chunk += 32 * stride) {
+        double sig_mine = 0.0;
+        if (NOISE != kNoiseNone) {
+            const long fl = f_chunk + lane * stride;
+            if (fl < p.n_frames) sig_mine = __dsqrt_rn((double)__fdiv_rn(p.power[fl], p.snr_lin));   // :647, :651
+        }
+        float c_e2 = 0.f, c_evm = 0.f;
+        for (int kk = 0; kk < 32; ++kk, ++k) {
+            const long f = f_chunk + kk * stride;
+            if (f >= p.n_frames) break;
+            const int s = (int)(k % kStages);
+            const uint32_t phase = (uint32_t)((k / kStages) & 1);
+            const double sigma_d = NOISE != kNoiseNone ? __shfl_sync(0xffffffffu, sig_mine, kk) : 0.0;
+            const float sigma_f = (float)sigma_d;
+            // this frame's payload words for the lane's three items (used after the transform)
+            const uint32_t *wb = p.tx_bits + f * 6;
+            const uint32_t w0 = wb[ic.word[0]], w1 = wb[ic.word[1]], w2 = wb[ic.word[2]];
+            float z[8];
+            if (NOISE == kNoisePhilox) {
+                float za[4], zb[4];
+                philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)blk_base, kDomainNoise, za);
+                philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)(blk_base + 8), kDomainNoise, zb);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
+            }
+            tma::wait(&ws.bar[s], phase);
+            float2 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = slot_m<EXACT>(i);
+                float2 smp = ws.st[s].x[grp][u + 8 * m];
+                if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
+                if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
+                v[i] = smp;
+            }
+            __syncwarp();                                         // every lane has its samples: the stage can be refilled
+            if (lane == 0 && f + kStages * stride < p.n_frames) issue(f + kStages * stride, s);
+            fft64<EXACT>(v, tw, tile, u);
+            float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[u + 8 * j] = v[j];
+            __syncwarp();
+            float f_e2 = 0.f;
+            uint32_t pk = 0;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848
+                const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
+                pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], w >> ic.shift[t], f_e2);
+            }
+            __syncwarp();
+            const bool any_err = __any_sync(0xffffffffu, pk != 0u);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) f_e2 += __shfl_xor_sync(0xffffffffu, f_e2, o);
+            float evm;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(evm) : "f"(f_e2 * inv_ref2));                                              // :1124
+            a_i += pk & 0xFFu; a_q += (pk >> 8) & 0xFFu; a_both += pk >> 16;
+            a_ferr += any_err; a_frames += 1;
+            c_e2 += f_e2; c_evm += evm;
+        }
+        a_e2 += (double)c_e2; a_evm += (double)c_evm;
+    }
+    if (p.counters == nullptr) return;
+    const uint32_t t_i = warp_sum(a_i), t_q = warp_sum(a_q), t_both = warp_sum(a_both);
+    if (lane == 0) {
+        s_cnt[warp][0] = (unsigned long long)t_i + 2ull * t_q - 2ull * t_both;     // bit errors (map of :423-430)
+        s_cnt[warp][1] = (unsigned long long)t_i + t_q;
+        s_cnt[warp][2] = a_ferr; s_cnt[warp][3] = a_frames;
+        s_sum[warp][0] = a_e2; s_sum[warp][1] = a_evm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long c[4] = {0, 0, 0, 0}; double sm[2] = {0, 0};
+        for (int w = 0; w < kWarpsPerBlock; ++w) {
+            for (int i = 0; i < 4; ++i) c[i] += s_cnt[w][i];
+            for (int i = 0; i < 2; ++i) sm[i] += s_sum[w][i];
+        }
+        if (c[3] != 0) {
+            ofdm_counters *o = p.counters;
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->bit_errors), c[0]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->rail_errors), c[1]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames_in_error), c[2]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames), c[3]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->bits), c[3] * 192ull);
+            atomicAdd(&o->sum_err2, sm[0]);
+            atomicAdd(&o->sum_ref2, (double)c[3] * ref2_frame);
+            atomicAdd(&o->sum_evm_lin, sm[1]);
+        }
+    }
+}
+
+inline size_t stream_smem_bytes() { return sizeof(StreamWarp) * kWarpsPerBlock; }
 
 }  // namespace ofdm

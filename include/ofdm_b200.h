@@ -94,6 +94,8 @@ const char *ofdm_last_error(const ofdm_ctx *ctx);
 int ofdm_ctx_set_stream(ofdm_ctx *ctx, void *cuda_stream);   /* run on a caller-owned cudaStream_t */
 void *ofdm_ctx_stream(const ofdm_ctx *ctx);
 int ofdm_ctx_sync(ofdm_ctx *ctx);
+/* tuning / testing knobs: "force_generic_rx" = 1 routes every receiver call through the generic kernel */
+int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value);
 int ofdm_ctx_sm_count(const ofdm_ctx *ctx);
 uint64_t ofdm_ctx_launch_count(const ofdm_ctx *ctx);          /* kernels launched so far by this ctx */
 int ofdm_dev_alloc(ofdm_ctx *ctx, void **ptr, size_t bytes);

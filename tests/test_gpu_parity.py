@@ -141,3 +141,32 @@ def test_receiver_fast(ofdm, pkg, port, n_sym, snr):
     evm_gpu = np.sqrt(cnt.sum_err2 / cnt.sum_ref2)
     evm_cpu = np.sqrt(np.sum(want["evm_lin"].astype(np.float64) ** 2) / n_frames)
     assert abs(evm_gpu - evm_cpu) <= 20 * REL * evm_cpu
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_streaming_kernel_equals_generic_kernel(ofdm, pkg, port, mode):
+    """n_sym == 2 sweeps run the TMA-staged kernel (k_stream_rx2); it must give the generic kernel's totals
+    (bit-identical integers in both modes: same arithmetic, different staging) for all three noise sources,
+    including frame counts that do not fill the last chunk / stage ring."""
+    for n_frames in (1, 2, 3, 777, 5000):
+        bits, g = bits_and_noise(300 + n_frames, n_frames, 2)
+        packed = ofdm.to_dev(pkg.pack_bits_host(bits).view(np.int32))
+        gd = ofdm.to_dev(g)
+        frames, power = ofdm.tx_frames(packed, 2, mode)
+        ota = ofdm.awgn_inject(frames, gd, 6.0, 2, mode, power=power)
+        res = {}
+        for generic in (1, 0):
+            ofdm.set_option("force_generic_rx", generic)
+            a, _ = ofdm.awgn_rx_inject(frames, gd, packed, 6.0, 2, mode, power=power)
+            b, _ = ofdm.awgn_rx_philox(frames, packed, 6.0, 11, 3, 1000, 2, mode, power=power)
+            c, _ = ofdm.rx_frames(ota, packed, 2, mode)
+            res[generic] = (a, b, c)
+        ofdm.set_option("force_generic_rx", 0)
+        for x, y in zip(res[0], res[1]):
+            assert (x.bit_errors, x.rail_errors, x.frames_in_error, x.frames, x.bits) == \
+                   (y.bit_errors, y.rail_errors, y.frames_in_error, y.frames, y.bits)
+            assert abs(x.sum_err2 - y.sum_err2) <= 1e-5 * y.sum_err2 and abs(x.sum_evm_lin - y.sum_evm_lin) <= 1e-4 * y.sum_evm_lin
+        # inject == (awgn then rx) on the same draws
+        assert res[0][0].bit_errors == res[0][2].bit_errors
+        if mode == pkg.MODE_EXACT:
+            assert res[0][0].bit_errors == port.chain(bits, g, 2, 6.0).bit_errors
