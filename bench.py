@@ -176,6 +176,49 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def run_extras(o, pkg, torch, dev, args, rank, world):
+    """Secondary configurations (not the headline): configs[2] streaming TX / RX of HBM-resident frames in fast
+    mode as HBM GB/s, configs[3] fused on-chip Philox Monte-Carlo as symbols/s.  Per-rank numbers (rank 0 reports)."""
+    import torch.distributed as dist
+    out = {}
+    peak, _ = peaks()
+
+    def timed(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n = args.stream_frames
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n * N_SYM * 3,), dtype=torch.int32, device=dev)
+    frames = torch.empty((n, pkg.frame_len(N_SYM), 2), dtype=torch.float32, device=dev)
+    cnt = o.new_counters(1)
+    lib, h = o.lib, o.h
+    ms_tx = timed(lambda: o._check(lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), None, n, N_SYM, pkg.MODE_FAST)))
+    ms_rx = timed(lambda: o._check(lib.ofdm_rx_frames(h, frames.data_ptr(), bits.data_ptr(), n, N_SYM, pkg.MODE_FAST, cnt.data_ptr(), None)))
+    tx_bytes, rx_bytes = n * (24 + 2560), n * (2048 + 24)
+    out["cfg2_streaming_fast"] = {
+        "frames": n, "data_symbols": n * N_SYM,
+        "tx_ms": ms_tx, "tx_GBps": tx_bytes / ms_tx / 1e6, "tx_frac_of_hbm_peak": tx_bytes / ms_tx / 1e6 / peak,
+        "rx_ms": ms_rx, "rx_GBps": rx_bytes / ms_rx / 1e6, "rx_frac_of_hbm_peak": rx_bytes / ms_rx / 1e6 / peak,
+        "symbols_per_s_tx_plus_rx": n * N_SYM / ((ms_tx + ms_rx) * 1e-3),
+        "bytes_per_frame": {"tx": 24 + 2560, "rx": 2048 + 24},
+        "note": "rx reads only the LTS halves and symbol bodies (2048 B of the 2560 B frame) + 24 B of bits"}
+    del frames, bits
+    torch.cuda.empty_cache()
+    nm = args.mc_frames
+    mc = o.new_counters(len(SNRS))
+    for mode, name in ((pkg.MODE_FAST, "fast"), (pkg.MODE_EXACT, "exact")):
+        ms = timed(lambda: o.mc_sweep_philox(7, rank * nm, nm, N_SYM, SNRS, mode, counters=mc), reps=2)
+        out["cfg3_mc_philox_" + name] = {"frames": nm, "snr_points": len(SNRS), "ms": ms,
+                                         "symbols_per_s": nm * N_SYM * len(SNRS) / (ms * 1e-3),
+                                         "fft_gflops": nm * len(SNRS) * 4 * 1920 / (ms * 1e-3) / 1e9}
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -270,6 +313,7 @@ def run_gpu(args):
     e2e_ms_total = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)   # wall clock covers the host side of the call
     clocks = sampler.stop() if rank == 0 else None
 
+    extras = run_extras(o, pkg, torch, dev, args, rank, world) if args.extras else None
     tm = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -309,6 +353,8 @@ def run_gpu(args):
                              "kernel_share_of_step": k_ms * n_snr / ms_step},
                 "clocks": clocks,
                 "ber_0_10_20dB": [ber[0], ber[10], ber[20]]}
+        if extras:
+            line["extras"] = extras
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
         print(json.dumps(line), flush=True)
@@ -327,6 +373,9 @@ def main():
     ap.add_argument("--frames", type=int, default=1_000_000, help="frames per GPU")
     ap.add_argument("--cpu-sample", type=int, default=4000, help="frames in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also measure configs[2] (streaming) and configs[3] (Philox MC)")
+    ap.add_argument("--stream-frames", type=int, default=8_388_608, help="frames for the streaming extra (16 Mi data symbols)")
+    ap.add_argument("--mc-frames", type=int, default=2_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -91,6 +91,9 @@ SIGNATURES = {
     "ofdm_random_bits": (_I, [_VP, _U32, _U64, _L, _I, _VP]),
     "ofdm_mc_sweep_philox_dev": (_I, [_VP, _U32, _U64, _L, _I, _VP, _I, _I, _VP]),
     "ofdm_mc_sweep_philox": (_I, [_VP, _U32, _U64, _L, _I, _VP, _I, _I, C.POINTER(Counters)]),
+    "ofdm_multipath_taps": (_I, [_VP, _VP, _VP, _I, _VP, _L, _I]),
+    "ofdm_multipath_philox": (_I, [_VP, _VP, _U32, _U64, _I, _VP, _VP, _L, _I]),
+    "ofdm_mc_sweep_multipath_dev": (_I, [_VP, _U32, _U64, _L, _I, _I, _VP, _I, _I, _VP]),
     "ofdm_counters_finalize": (_I, [C.POINTER(Counters), C.POINTER(_F)]),
     "ofdm_write_float_array_to_file": (_I, [_VP, _I, C.c_char_p]),
     "ofdm_write_complex_array_to_file": (_I, [_VP, _I, C.c_char_p, _I]),
@@ -334,6 +337,24 @@ class Ofdm:
         out = (Counters * len(snr))()
         self._check(self.lib.ofdm_mc_sweep_philox(self.h, seed, frame0, n_frames, n_sym, snr.ctypes.data, len(snr), mode, out))
         return list(out)
+
+    def multipath_taps(self, tx, taps, n_sym):
+        out = self.empty(tuple(tx.shape), self.torch.float32)
+        self._check(self.lib.ofdm_multipath_taps(self.h, _ptr(tx), _ptr(taps), taps.shape[1], _ptr(out), tx.shape[0], n_sym))
+        return out
+
+    def multipath_philox(self, tx, seed, frame0, n_taps, n_sym):
+        out = self.empty(tuple(tx.shape), self.torch.float32)
+        taps = self.empty((tx.shape[0], n_taps, 2), self.torch.float32)
+        self._check(self.lib.ofdm_multipath_philox(self.h, _ptr(tx), seed, frame0, n_taps, _ptr(out), _ptr(taps), tx.shape[0], n_sym))
+        return out, taps
+
+    def mc_sweep_multipath(self, seed, frame0, n_frames, n_sym, n_taps, snr_db, mode, counters=None):
+        snr = np.ascontiguousarray(snr_db, dtype=np.float32)
+        cnt = counters if counters is not None else self.new_counters(len(snr))
+        self._check(self.lib.ofdm_mc_sweep_multipath_dev(self.h, seed, frame0, n_frames, n_sym, n_taps, snr.ctypes.data, len(snr), mode,
+                                                         _ptr(cnt)))
+        return None if counters is not None else self.read_counters(cnt)
 
     def finalize(self, counters):
         res = (_F * 3)()

@@ -674,6 +674,69 @@ int ofdm_mc_sweep_philox(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_f
     return OFDM_OK;
 }
 
+// ------------------------------------------------------------------ multipath extension (configs[4])
+static int multipath_common(ofdm_ctx *ctx, bool philox, const float *tx, const float *taps, uint32_t seed, uint64_t frame0, int n_taps,
+                            float *out, float *taps_out, long n_frames, int n_sym)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && n_taps >= 1 && n_taps <= kMaxTaps);
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, tx != nullptr && out != nullptr && tx != out && (philox || taps != nullptr));
+    const int len = OFDM_FRAME_LEN(n_sym);
+    const size_t smem = (size_t)kWarpsPerBlock * (len + kMaxTaps) * sizeof(float2);
+    const float2 *x = reinterpret_cast<const float2 *>(tx), *h = reinterpret_cast<const float2 *>(taps);
+    float2 *y = reinterpret_cast<float2 *>(out), *ho = reinterpret_cast<float2 *>(taps_out);
+    if (philox) {
+        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = grid_for(ctx, k_multipath<true>, smem, kWarpsPerBlock, n_frames);
+        k_multipath<true><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len);
+    } else {
+        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = grid_for(ctx, k_multipath<false>, smem, kWarpsPerBlock, n_frames);
+        k_multipath<false><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len);
+    }
+    return check_launch(ctx, "k_multipath");
+}
+
+int ofdm_multipath_taps(ofdm_ctx *ctx, const float *tx, const float *taps, int n_taps, float *out, long n_frames, int n_sym)
+{
+    return multipath_common(ctx, false, tx, taps, 0, 0, n_taps, out, nullptr, n_frames, n_sym);
+}
+int ofdm_multipath_philox(ofdm_ctx *ctx, const float *tx, uint32_t seed, uint64_t frame0, int n_taps, float *out, float *taps_out,
+                          long n_frames, int n_sym)
+{
+    return multipath_common(ctx, true, tx, nullptr, seed, frame0, n_taps, out, taps_out, n_frames, n_sym);
+}
+
+int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps, const float *snr_db,
+                                int n_snr, int mode, ofdm_counters *counters)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0 && n_snr <= kMaxSnr && n_taps >= 1 && n_taps <= kMaxTaps);
+    if (n_frames == 0 || n_snr == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, snr_db != nullptr && counters != nullptr);
+    const int len = OFDM_FRAME_LEN(n_sym);
+    const long chunk = 1048576;
+    for (long f0 = 0; f0 < n_frames; f0 += chunk) {
+        const long n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        void *bits = nullptr, *frames = nullptr, *power = nullptr, *faded = nullptr;
+        if (int st = ensure_scratch(ctx, 4, (size_t)n * n_sym * 3 * sizeof(uint32_t), &bits)) return st;
+        if (int st = ensure_scratch(ctx, 1, (size_t)n * len * 2 * sizeof(float), &frames)) return st;
+        if (int st = ensure_scratch(ctx, 5, (size_t)n * len * 2 * sizeof(float), &faded)) return st;
+        if (int st = ensure_scratch(ctx, 2, (size_t)n * sizeof(float), &power)) return st;
+        const uint64_t fr0 = frame0 + (uint64_t)f0;
+        if (int st = ofdm_random_bits(ctx, seed, fr0, n, n_sym, (uint32_t *)bits)) return st;
+        if (int st = ofdm_tx_frames(ctx, (const uint32_t *)bits, (float *)frames, nullptr, n, n_sym, mode)) return st;
+        if (int st = ofdm_multipath_philox(ctx, (const float *)frames, seed, fr0, n_taps, (float *)faded, nullptr, n, n_sym)) return st;
+        if (int st = frame_power(ctx, (const float *)faded, (float *)power, n, len, mode)) return st;      // power of what goes on the air
+        for (int i = 0; i < n_snr; ++i)
+            if (int st = ofdm_awgn_rx_philox(ctx, (const float *)faded, (const float *)power, (const uint32_t *)bits, snr_db[i], seed,
+                                             (uint32_t)i, fr0, n, n_sym, mode, counters + i, nullptr))
+                return st;
+    }
+    return OFDM_OK;
+}
+
 int ofdm_counters_finalize(const ofdm_counters *c, float res[3])
 {
     if (!c || !res) return OFDM_ERR_INVALID;

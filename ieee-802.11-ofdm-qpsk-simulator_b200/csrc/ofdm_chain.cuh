@@ -264,6 +264,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
 }
+__device__ __forceinline__ void wait_addr(uint32_t bar_saddr, uint32_t phase)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(bar_saddr), "r"(phase) : "memory");
+}
 __device__ __forceinline__ void wait(uint64_t *bar, uint32_t phase)
 {
     asm volatile("{\n"
@@ -309,20 +320,26 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
     const float inv_ref2 = (float)(1.0 / ref2_frame);
     constexpr uint32_t kBytes = 4 * 512 + (NOISE == kNoiseInject ? 4 * 256 : 0);
 
-    auto issue = [&](long f, int s) {          // lane 0 only
-        const float2 *x = p.in + f * len;
-        tma::expect_tx(&ws.bar[s], kBytes);
-        tma::bulk_g2s(ws.st[s].x[0], x + 32, 512, &ws.bar[s]);           // Channel_Estimation :837
-        tma::bulk_g2s(ws.st[s].x[1], x + 96, 512, &ws.bar[s]);           //                    :838
-        tma::bulk_g2s(ws.st[s].x[2], x + 176, 512, &ws.bar[s]);          // CP strip :1028 (symbol 0)
-        tma::bulk_g2s(ws.st[s].x[3], x + 256, 512, &ws.bar[s]);          //                (symbol 1)
-        if (NOISE == kNoiseInject) {
-            const float *g = p.g + f * len;
-            tma::bulk_g2s(ws.st[s].g[0], g + 32, 256, &ws.bar[s]);
-            tma::bulk_g2s(ws.st[s].g[1], g + 96, 256, &ws.bar[s]);
-            tma::bulk_g2s(ws.st[s].g[2], g + 176, 256, &ws.bar[s]);
-            tma::bulk_g2s(ws.st[s].g[3], g + 256, 256, &ws.bar[s]);
-        }
+    // Lanes 0..3 each own one IQ window copy, lanes 4..7 one draw window copy: a stage refill is one expect_tx
+    // plus ONE bulk-copy instruction issued by up to eight lanes, all addresses per-lane constants.
+    constexpr int kCopyLanes = NOISE == kNoiseInject ? 8 : 4;
+    const int cw = lane & 3;
+    const bool c_is_g = lane >= 4;
+    const int c_off = cw == 0 ? 32 : cw == 1 ? 96 : cw == 2 ? 176 : 256;                 // :837, :838, :1028
+    const char *c_src0 = c_is_g ? reinterpret_cast<const char *>(p.g) + (size_t)c_off * 4
+                                : reinterpret_cast<const char *>(p.in) + (size_t)c_off * 8;
+    const long c_fstride = c_is_g ? len * 4 : len * 8;
+    const uint32_t c_bytes = c_is_g ? 256u : 512u;
+    const uint32_t c_dst0 = c_is_g ? tma::saddr(ws.st[0].g[cw]) : tma::saddr(ws.st[0].x[cw]);
+    const uint32_t bar0 = tma::saddr(&ws.bar[0]);
+    auto issue = [&](long f, int s) {          // whole warp calls; lanes < kCopyLanes act
+        const uint32_t bar = bar0 + 8u * (uint32_t)s;
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBytes) : "memory");
+        if (lane < kCopyLanes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(c_dst0 + (uint32_t)s * (uint32_t)sizeof(StreamStage)), "l"(c_src0 + f * c_fstride), "r"(c_bytes), "r"(bar)
+                         : "memory");
     };
 
     if (lane == 0) {
@@ -330,9 +347,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
         tma::fence_mbar_init();
     }
     __syncwarp();
-    if (lane == 0)
-        for (int s = 0; s < kStages; ++s)
-            if (f_first + s * stride < p.n_frames) issue(f_first + s * stride, s);
+    for (int s = 0; s < kStages; ++s)
+        if (f_first + s * stride < p.n_frames) issue(f_first + s * stride, s);
 
     uint32_t a_i = 0, a_q = 0, a_both = 0, a_ferr = 0, a_frames = 0;
     double a_e2 = 0.0, a_evm = 0.0;
@@ -363,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
 #pragma unroll
                 for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
             }
-            tma::wait(&ws.bar[s], phase);
+            tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
             float2 v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -374,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
                 v[i] = smp;
             }
             __syncwarp();                                         // every lane has its samples: the stage can be refilled
-            if (lane == 0 && f + kStages * stride < p.n_frames) issue(f + kStages * stride, s);
+            if (f + kStages * stride < p.n_frames) issue(f + kStages * stride, s);
             fft64<EXACT>(v, tw, tile, u);
             float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
 #pragma unroll
@@ -431,5 +447,53 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
 }
 
 inline size_t stream_smem_bytes() { return sizeof(StreamWarp) * kWarpsPerBlock; }
+
+}  // namespace ofdm
+
+namespace ofdm {
+// ------------------------------------------------------------------------------------------------
+// configs[4] extension (no counterpart in the reference): per-frame multipath channel
+// y[n] = sum_l h[l] x[n-l], x[n<0] = 0, n_taps <= 16 = CP length (no inter-symbol interference, the LTS
+// estimate + one-tap equaliser of :830-850, :1046-1052 absorb it).  Taps are either supplied
+// ([frames][n_taps] complex) or drawn on chip: i.i.d. complex Gaussian, E|h_l|^2 = 1/n_taps, Philox domain 2,
+// tap l = normals (2l, 2l+1) of block l/2.  Same float operation order as the oracle (orc_apply_taps):
+// descending l, separate multiplies and adds (no FMA), so supplied taps reproduce it bit for bit.
+constexpr int kMaxTaps = 16;
+
+template <bool PHILOX>
+__global__ void __launch_bounds__(kThreads) k_multipath(const float2 *__restrict__ tx, const float2 *__restrict__ taps, uint32_t seed,
+                                                        uint64_t frame0, int n_taps, float2 *__restrict__ out, float2 *__restrict__ taps_out,
+                                                        long n_frames, int len)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * (len + kMaxTaps);
+    float2 *sh = sx + len;
+    const float scale = sqrtf(0.5f / (float)n_taps);
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float2 *x = tx + f * len;
+        for (int i = lane; i < len; i += 32) sx[i] = x[i];
+        if (PHILOX) {
+            if (2 * lane < n_taps) {
+                float z[4];
+                philox_normals4(seed, 0u, frame0 + (uint64_t)f, (uint32_t)lane, kDomainTaps, z);
+                sh[2 * lane] = make_float2(scale * z[0], scale * z[1]);
+                if (2 * lane + 1 < n_taps) sh[2 * lane + 1] = make_float2(scale * z[2], scale * z[3]);
+            }
+        } else if (lane < n_taps) sh[lane] = taps[f * n_taps + lane];
+        __syncwarp();
+        if (taps_out != nullptr && lane < n_taps) taps_out[f * n_taps + lane] = sh[lane];
+        for (int n = lane; n < len; n += 32) {
+            float ar = 0.f, ai = 0.f;
+            for (int l = (n_taps - 1 < n ? n_taps - 1 : n); l >= 0; --l) {
+                const float2 a = sx[n - l], b = sh[l];
+                ar = __fadd_rn(ar, __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)));
+                ai = __fadd_rn(ai, __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+            }
+            out[f * len + n] = make_float2(ar, ai);
+        }
+        __syncwarp();
+    }
+}
 
 }  // namespace ofdm

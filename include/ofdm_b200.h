@@ -172,6 +172,20 @@ int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long
 int ofdm_mc_sweep_philox(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym,
                          const float *snr_db, int n_snr, int mode, ofdm_counters *out_host);
 
+/* ---- multipath extension (BASELINE configs[4]; the reference's only channel is AWGN, OFDM.c:635-655) ----
+ * y[n] = sum_l h[l] x[n-l] per frame, n_taps <= 16 (= CP length), applied between the transmitter and
+ * Transmission_Over_Air; the reference's own LTS estimate + one-tap equaliser (OFDM.c:830-850, 1046-1052) undo it.
+ * _taps: taps supplied, [n_frames][n_taps] complex; _philox: drawn on chip (i.i.d. CN(0, 1/n_taps), Philox
+ * domain 2), optionally written to taps_out_dev.  out_dev must differ from tx_dev. */
+int ofdm_multipath_taps(ofdm_ctx *ctx, const float *tx_dev, const float *taps_dev, int n_taps, float *out_dev,
+                        long n_frames, int n_sym);
+int ofdm_multipath_philox(ofdm_ctx *ctx, const float *tx_dev, uint32_t seed, uint64_t frame0, int n_taps,
+                          float *out_dev, float *taps_out_dev, long n_frames, int n_sym);
+/* Monte-Carlo sweep through the multipath channel (bits, taps and noise from the Philox streams), accumulating
+ * into device counters [n_snr]; the signal power of OFDM.c:637-643 is measured after the channel. */
+int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps,
+                                const float *snr_db, int n_snr, int mode, ofdm_counters *counters_dev);
+
 /* Res[3] = {EVM_dB, EVM_AGC_dB, BER} of OFDM.c:1163-1165 from batch totals */
 int ofdm_counters_finalize(const ofdm_counters *c, float res[3]);
 
