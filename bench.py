@@ -163,7 +163,7 @@ def run_reference(args):
             "config": {"workload": workload_name(args.frames), "reference_arm_sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -357,14 +357,26 @@ def run_gpu(args):
             line["extras"] = extras
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample)
-        print(json.dumps(line), flush=True)
+        emit(line)
     o.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def emit(line):
+    """print the one JSON line on the real stdout (libraries such as NCCL may write to fd 1 meanwhile)"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # anything else that prints to stdout goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -163,7 +163,7 @@ template <bool EXACT, int NOISE>
 int launch_stream(ofdm_ctx *ctx, const RxParams &p)
 {
     auto k = k_stream_rx2<EXACT, NOISE>;
-    const size_t smem = stream_smem_bytes();
+    const size_t smem = stream_smem_bytes<NOISE>();
     OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
     k<<<grid, kThreads, smem, ctx->stream>>>(p);

@@ -264,6 +264,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void expect_tx_addr(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_addr(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void wait_addr(uint32_t bar_saddr, uint32_t phase)
 {
     asm volatile("{\n"
@@ -290,56 +305,71 @@ __device__ __forceinline__ void wait(uint64_t *bar, uint32_t phase)
 
 constexpr int kStages = 2;
 
-struct StreamStage {
+template <bool WITH_DRAWS> struct alignas(16) StreamStage {     // bulk-copy destinations must be 16-byte aligned
     float2 x[4][kWin];              // LTS1, LTS2, sym0 body, sym1 body (skewed windows)
     float g[4][kWin];               // the matching draws (injected noise only)
 };
-struct StreamWarp {
+template <> struct alignas(16) StreamStage<false> {
+    float2 x[4][kWin];
+    float g[1][4];                  // never touched
+};
+template <bool WITH_DRAWS> struct alignas(16) StreamWarp {
     float2 tile[kWarpTile];
     float2 lts[2][kWin];
-    StreamStage st[kStages];
+    StreamStage<WITH_DRAWS> st[kStages];
     uint64_t bar[kStages];
 };
+// resident blocks per SM the launch bounds ask for: the fp32 kernels fit three (80 registers, <= 75 KB shared)
+static_assert(sizeof(StreamStage<false>) % 16 == 0 && sizeof(StreamStage<true>) % 16 == 0 && sizeof(StreamWarp<false>) % 16 == 0, "stage alignment");
+template <bool EXACT, int NOISE> constexpr int stream_blocks_per_sm() { return (!EXACT && NOISE != kNoiseInject) ? 3 : 2; }
 
 template <bool EXACT, int NOISE>
-__global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
+__global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<EXACT, NOISE>()) k_stream_rx2(RxParams p)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
     __shared__ double s_sum[kWarpsPerBlock][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
-    StreamWarp &ws = reinterpret_cast<StreamWarp *>(s_raw)[warp];
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);                  // same value, provably warp-uniform
+    using SW = StreamWarp<NOISE == kNoiseInject>;
+    using SS = StreamStage<NOISE == kNoiseInject>;
+    SW &ws = reinterpret_cast<SW *>(s_raw)[warp];
+    SW &ws_u = reinterpret_cast<SW *>(s_raw)[warp_u];
     float2 *tile = ws.tile + grp * kGroupPitch;
     Tw<EXACT> tw; tw.load(u);
     const ItemConst ic = make_items(lane);
     constexpr int len = 320;
     const long stride = (long)gridDim.x * kWarpsPerBlock;
-    const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp;
+    const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp_u;
     const double q = (double)kQpsk;
     const double ref2_frame = 96.0 * (2.0 * q * q);
     const float inv_ref2 = (float)(1.0 / ref2_frame);
     constexpr uint32_t kBytes = 4 * 512 + (NOISE == kNoiseInject ? 4 * 256 : 0);
 
-    // Lanes 0..3 each own one IQ window copy, lanes 4..7 one draw window copy: a stage refill is one expect_tx
-    // plus ONE bulk-copy instruction issued by up to eight lanes, all addresses per-lane constants.
-    constexpr int kCopyLanes = NOISE == kNoiseInject ? 8 : 4;
-    const int cw = lane & 3;
-    const bool c_is_g = lane >= 4;
-    const int c_off = cw == 0 ? 32 : cw == 1 ? 96 : cw == 2 ? 176 : 256;                 // :837, :838, :1028
-    const char *c_src0 = c_is_g ? reinterpret_cast<const char *>(p.g) + (size_t)c_off * 4
-                                : reinterpret_cast<const char *>(p.in) + (size_t)c_off * 8;
-    const long c_fstride = c_is_g ? len * 4 : len * 8;
-    const uint32_t c_bytes = c_is_g ? 256u : 512u;
-    const uint32_t c_dst0 = c_is_g ? tma::saddr(ws.st[0].g[cw]) : tma::saddr(ws.st[0].x[cw]);
-    const uint32_t bar0 = tma::saddr(&ws.bar[0]);
-    auto issue = [&](long f, int s) {          // whole warp calls; lanes < kCopyLanes act
-        const uint32_t bar = bar0 + 8u * (uint32_t)s;
-        if (lane == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBytes) : "memory");
-        if (lane < kCopyLanes)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(c_dst0 + (uint32_t)s * (uint32_t)sizeof(StreamStage)), "l"(c_src0 + f * c_fstride), "r"(c_bytes), "r"(bar)
-                         : "memory");
+    // A stage refill = one expect_tx + four (eight with draws) bulk copies, issued by one elected lane.  UBLKCP takes
+    // uniform-register operands, so every operand is derived from warp-uniform values (the warp index is
+    // broadcast with a shuffle so that the compiler can prove it) and stays on the uniform datapath.
+    const uint32_t stage0 = tma::saddr(&ws_u.st[0]);
+    const uint32_t bar0 = tma::saddr(&ws_u.bar[0]);
+    auto issue = [&](long f, int s) {          // f, s warp-uniform; whole warp calls
+        if (tma::elect_one()) {
+            const uint32_t bar = bar0 + 8u * (uint32_t)s;
+            const uint32_t dst = stage0 + (uint32_t)s * (uint32_t)sizeof(SS);
+            const char *x = reinterpret_cast<const char *>(p.in) + f * (len * 8);
+            tma::expect_tx_addr(bar, kBytes);
+            tma::bulk_addr(dst + 0 * kWin * 8, x + 32 * 8, 512, bar);             // Channel_Estimation :837
+            tma::bulk_addr(dst + 1 * kWin * 8, x + 96 * 8, 512, bar);             //                    :838
+            tma::bulk_addr(dst + 2 * kWin * 8, x + 176 * 8, 512, bar);            // CP strip :1028, symbol 0
+            tma::bulk_addr(dst + 3 * kWin * 8, x + 256 * 8, 512, bar);            //                 symbol 1
+            if (NOISE == kNoiseInject) {
+                const char *g = reinterpret_cast<const char *>(p.g) + f * (len * 4);
+                const uint32_t gd = dst + 4 * kWin * 8;
+                tma::bulk_addr(gd + 0 * kWin * 4, g + 32 * 4, 256, bar);
+                tma::bulk_addr(gd + 1 * kWin * 4, g + 96 * 4, 256, bar);
+                tma::bulk_addr(gd + 2 * kWin * 4, g + 176 * 4, 256, bar);
+                tma::bulk_addr(gd + 3 * kWin * 4, g + 256 * 4, 256, bar);
+            }
+        }
     };
 
     if (lane == 0) {
@@ -446,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rx2(RxParams p)
     }
 }
 
-inline size_t stream_smem_bytes() { return sizeof(StreamWarp) * kWarpsPerBlock; }
+template <int NOISE> inline size_t stream_smem_bytes() { return sizeof(StreamWarp<NOISE == kNoiseInject>) * kWarpsPerBlock; }
 
 }  // namespace ofdm
 

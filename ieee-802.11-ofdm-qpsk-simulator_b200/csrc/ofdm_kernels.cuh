@@ -110,12 +110,15 @@ __global__ void __launch_bounds__(kThreads) k_tx_frames(const uint32_t *__restri
                                                         long n_frames, int n_sym)
 {
     __shared__ float2 s_tile[kWarpsPerBlock][kWarpTile];
+    __shared__ __align__(16) float2 s_lts_time[160];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
     float2 *tile = s_tile[warp] + grp * kGroupPitch;
     Tw<EXACT> tw; tw.load(u);
     int dmap[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dmap[i] = c_tab.bin_data[8 * slot_m<EXACT>(i) + u];   // input index n <-> centred (n+32)%64
+    for (int i = threadIdx.x; i < 160; i += kThreads) s_lts_time[i] = c_tab.lts_time[i];
+    __syncthreads();
     const int len = 160 + 80 * n_sym;
     const long n_symbols = n_frames * n_sym;
     const long n_groups = (long)gridDim.x * kWarpsPerBlock * 4;
@@ -149,8 +152,10 @@ __global__ void __launch_bounds__(kThreads) k_tx_frames(const uint32_t *__restri
                 if (np >= 48) dst[np - 48] = y;                 // CP   :563
             }
             if (s == 0) {                                       // LTS slot :573 (constant, built at context creation)
+                const float4 *src4 = reinterpret_cast<const float4 *>(s_lts_time);
+                float4 *dst4 = reinterpret_cast<float4 *>(fr);              // frames are 2560 B: 16-byte aligned
 #pragma unroll
-                for (int k = 0; k < 20; ++k) fr[u + 8 * k] = c_tab.lts_time[u + 8 * k];
+                for (int k = 0; k < 10; ++k) dst4[u + 8 * k] = src4[u + 8 * k];
             }
         }
     }
