@@ -15,11 +15,14 @@ struct ofdm_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
+    cudaStream_t copy_stream = nullptr;          // H2D pipeline of ofdm_sweep_inject_host
+    cudaEvent_t copy_done[2] = {nullptr, nullptr}, call_start = nullptr;
     uint64_t launches = 0;
     bool force_generic = false;      // testing knob: route n_sym == 2 sweeps through the generic kernel too
     char err[256] = {0};
     float lts_freq[128];
     float lts_time[320];
+    float lts_power_prefix = 0.0f;
     // cached scratch (grown on demand, released with the context)
     void *scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -128,6 +131,7 @@ int upload_tables(ofdm_ctx *ctx, const float *lts_time /* nullable */)
             sum += (double)lts_time[2 * i] * lts_time[2 * i] + (double)lts_time[2 * i + 1] * lts_time[2 * i + 1];
         }
         t.lts_power_prefix = acc;
+        ctx->lts_power_prefix = acc;
         t.lts_power_sum = (float)sum;
     }
     OFDM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -196,14 +200,20 @@ int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
     return launch_rx_d<false, kNoisePhilox>(ctx, dump, p);
 }
 
-int frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames, int len, int mode)
+int blocks_1d(long n) { return (int)((n + 255) / 256); }
+
+int frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames, int len, int mode, bool lts_prefix = false)
 {
     if (mode == OFDM_MODE_EXACT) {
-        size_t smem = (size_t)kWarpsPerBlock * len * sizeof(double);
-        if (smem > 48 * 1024)
-            OFDM_CUDA(ctx, cudaFuncSetAttribute(k_frame_power_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int grid = grid_for(ctx, k_frame_power_exact, smem, kWarpsPerBlock, n_frames);
-        k_frame_power_exact<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), power, n_frames, len);
+        // frames straight from the transmitter start with the LTS slot, whose partial sum is a build constant
+        const bool vec_ok = ((uintptr_t)frames % 16 == 0) && (len % 2 == 0);
+        const bool skip = lts_prefix && vec_ok;
+        const float2 *x = reinterpret_cast<const float2 *>(frames);
+        if (vec_ok)
+            k_frame_power_exact<true><<<blocks_1d(n_frames), 256, 0, ctx->stream>>>(x, power, n_frames, len, skip ? 160 : 0,
+                                                                                  skip ? ctx->lts_power_prefix : 0.0f);
+        else
+            k_frame_power_exact<false><<<blocks_1d(n_frames), 256, 0, ctx->stream>>>(x, power, n_frames, len, 0, 0.0f);
         return check_launch(ctx, "k_frame_power_exact");
     }
     int grid = grid_for(ctx, k_frame_power_fast, 0, kWarpsPerBlock, n_frames);
@@ -214,7 +224,6 @@ int frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames,
 bool mode_ok(int mode) { return mode == OFDM_MODE_EXACT || mode == OFDM_MODE_FAST; }
 bool nsym_ok(int n_sym) { return n_sym >= 1 && n_sym <= OFDM_MAX_SYM; }
 
-int blocks_1d(long n) { return (int)((n + 255) / 256); }
 
 }  // namespace
 
@@ -283,6 +292,12 @@ int ofdm_ctx_destroy(ofdm_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 6; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->copy_done[i]);
+        cudaEventDestroy(ctx->call_start);
+    }
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return OFDM_OK;
@@ -467,7 +482,7 @@ int ofdm_tx_frames(ofdm_ctx *ctx, const uint32_t *bits, float *frames, float *po
         st = check_launch(ctx, "k_tx_frames<fast>");
     }
     if (st != OFDM_OK || power == nullptr) return st;
-    return frame_power(ctx, frames, power, n_frames, OFDM_FRAME_LEN(n_sym), mode);
+    return frame_power(ctx, frames, power, n_frames, OFDM_FRAME_LEN(n_sym), mode, true);
 }
 
 static int resolve_power(ofdm_ctx *ctx, const float *tx, const float *power, long n_frames, int len, int mode, const float **out)
@@ -592,15 +607,45 @@ int ofdm_sweep_inject_host(ofdm_ctx *ctx, const uint32_t *bits_host, const float
     if (int st = bind(ctx)) return st;
     OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0);
     if (n_frames == 0 || n_snr == 0) return ofdm_sweep_inject_dev(ctx, nullptr, nullptr, n_frames, n_sym, snr_db, n_snr, mode, out_host);
-    OFDM_REQUIRE(ctx, bits_host != nullptr && g_host != nullptr);
+    OFDM_REQUIRE(ctx, bits_host != nullptr && g_host != nullptr && snr_db != nullptr && out_host != nullptr);
     const int len = OFDM_FRAME_LEN(n_sym);
-    void *bits = nullptr, *g = nullptr;
-    const size_t bits_bytes = (size_t)n_frames * n_sym * 3 * sizeof(uint32_t), g_bytes = (size_t)n_frames * len * sizeof(float);
-    if (int st = ensure_scratch(ctx, 4, bits_bytes, &bits)) return st;
-    if (int st = ensure_scratch(ctx, 5, g_bytes, &g)) return st;
-    OFDM_CUDA(ctx, cudaMemcpyAsync(bits, bits_host, bits_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    OFDM_CUDA(ctx, cudaMemcpyAsync(g, g_host, g_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return ofdm_sweep_inject_dev(ctx, (const uint32_t *)bits, (const float *)g, n_frames, n_sym, snr_db, n_snr, mode, out_host);
+    void *bits = nullptr, *g = nullptr, *frames = nullptr, *power = nullptr, *cnt = nullptr;
+    const size_t bits_per_frame = (size_t)n_sym * 3 * sizeof(uint32_t), g_per_frame = (size_t)len * sizeof(float);
+    if (int st = ensure_scratch(ctx, 4, (size_t)n_frames * bits_per_frame, &bits)) return st;
+    if (int st = ensure_scratch(ctx, 5, (size_t)n_frames * g_per_frame, &g)) return st;
+    if (int st = ensure_scratch(ctx, 1, (size_t)n_frames * len * 2 * sizeof(float), &frames)) return st;
+    if (int st = ensure_scratch(ctx, 2, (size_t)n_frames * sizeof(float), &power)) return st;
+    if (int st = ensure_scratch(ctx, 3, sizeof(ofdm_counters) * (size_t)n_snr, &cnt)) return st;
+    if (!ctx->copy_stream) {
+        OFDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) OFDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
+        OFDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->call_start, cudaEventDisableTiming));
+    }
+    // Host->device copies (copy stream) are pipelined against the sweep of the previous chunk (compute stream):
+    // chunk c's kernels wait only for chunk c's copies.  The scratch buffers may still be read by earlier work
+    // on the compute stream, so the copy stream first waits for everything enqueued there so far.
+    OFDM_CUDA(ctx, cudaEventRecord(ctx->call_start, ctx->stream));
+    OFDM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->call_start, 0));
+    OFDM_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(ofdm_counters) * (size_t)n_snr, ctx->stream));
+    const long chunk = 131072;
+    int c = 0;
+    for (long f0 = 0; f0 < n_frames; f0 += chunk, ++c) {
+        const long n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        char *db = (char *)bits + f0 * bits_per_frame, *dg = (char *)g + f0 * g_per_frame;
+        OFDM_CUDA(ctx, cudaMemcpyAsync(db, (const char *)bits_host + f0 * bits_per_frame, n * bits_per_frame, cudaMemcpyHostToDevice, ctx->copy_stream));
+        OFDM_CUDA(ctx, cudaMemcpyAsync(dg, (const char *)g_host + f0 * g_per_frame, n * g_per_frame, cudaMemcpyHostToDevice, ctx->copy_stream));
+        OFDM_CUDA(ctx, cudaEventRecord(ctx->copy_done[c & 1], ctx->copy_stream));
+        OFDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[c & 1], 0));
+        float *fr = (float *)frames + f0 * len * 2, *pw = (float *)power + f0;
+        if (int st = ofdm_tx_frames(ctx, (const uint32_t *)db, fr, pw, n, n_sym, mode)) return st;        // Transmitter(), OFDM.c:1191
+        for (int i = 0; i < n_snr; ++i)                                                                   // SNR loop, OFDM.c:1202-1222
+            if (int st = ofdm_awgn_rx_inject(ctx, fr, (const float *)dg, pw, (const uint32_t *)db, snr_db[i], n, n_sym, mode,
+                                             (ofdm_counters *)cnt + i, nullptr))
+                return st;
+    }
+    OFDM_CUDA(ctx, cudaMemcpyAsync(out_host, cnt, sizeof(ofdm_counters) * (size_t)n_snr, cudaMemcpyDeviceToHost, ctx->stream));
+    OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OFDM_OK;
 }
 
 // ------------------------------------------------------------------ Philox Monte-Carlo

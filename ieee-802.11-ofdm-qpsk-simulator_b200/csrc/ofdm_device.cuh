@@ -215,7 +215,7 @@ __device__ __forceinline__ double hypot_glibc(double x, double y)
 {
     x = fabs(x); y = fabs(y);
     double ax = x < y ? y : x, ay = x < y ? x : y;
-    if (ax >= __ddiv_rn(ay, 0x1p-54)) return __dadd_rn(ax, ay);
+    if (ax >= __dmul_rn(ay, 0x1p54)) return __dadd_rn(ax, ay);      // ay / EPS, EPS = 2^-54: exact scaling
     double h = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
     double t1, t2;
     if (h <= __dmul_rn(2.0, ay)) {

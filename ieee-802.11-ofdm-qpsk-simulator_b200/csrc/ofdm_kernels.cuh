@@ -161,29 +161,38 @@ __global__ void __launch_bounds__(kThreads) k_tx_frames(const uint32_t *__restri
     }
 }
 
-// signal power of Transmission_Over_Air OFDM.c:637-643.  EXACT: double terms cabs*cabs (glibc hypot),
-// accumulated sequentially into a float, one warp per frame (terms in parallel, chain on lane 0).
+// signal power of Transmission_Over_Air OFDM.c:637-643.  EXACT: double terms cabs*cabs (glibc hypot), accumulated
+// sequentially into a float.  The chain is inherently serial per frame, so every lane runs the chain of its own
+// frame (32 frames per warp in flight); a lane walks its frame 16 bytes at a time, so each 128-byte line it
+// touches is fetched once and served from L1 for the next seven loads.  `first` / `acc0` let the transmitter
+// skip the LTS slot, whose partial sum is a constant of the build (Tables::lts_power_prefix).
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_frame_power_exact(const float2 *__restrict__ frames, float *__restrict__ power,
-                                                                long n_frames, int len)
+                                                                long n_frames, int len, int first, float acc0)
 {
-    extern __shared__ double s_terms[];                         // [warps][len]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *terms = s_terms + (size_t)warp * len;
-    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+    const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    float p = acc0;
+    if (VEC) {
+        const float4 *x = reinterpret_cast<const float4 *>(frames + f * len + first);     // first and len are even, base 16-byte aligned
+        const int n2 = (len - first) >> 1;
+#pragma unroll 2
+        for (int i = 0; i < n2; ++i) {
+            const float4 s = x[i];
+            const double h0 = hypot_glibc((double)s.x, (double)s.y);
+            const double h1 = hypot_glibc((double)s.z, (double)s.w);
+            p = __double2float_rn(__dadd_rn((double)p, __dmul_rn(h0, h0)));
+            p = __double2float_rn(__dadd_rn((double)p, __dmul_rn(h1, h1)));
+        }
+    } else {
         const float2 *x = frames + f * len;
-        for (int i = lane; i < len; i += 32) {
-            float2 s = x[i];
-            double h = hypot_glibc((double)s.x, (double)s.y);
-            terms[i] = __dmul_rn(h, h);
+        for (int i = 0; i < len; ++i) {
+            const float2 s = x[i];
+            const double h = hypot_glibc((double)s.x, (double)s.y);
+            p = __double2float_rn(__dadd_rn((double)p, __dmul_rn(h, h)));
         }
-        __syncwarp();
-        if (lane == 0) {
-            float p = 0.f;
-            for (int i = 0; i < len; ++i) p = __double2float_rn(__dadd_rn((double)p, terms[i]));
-            power[f] = __fdiv_rn(p, (float)len);
-        }
-        __syncwarp();
     }
+    power[f] = __fdiv_rn(p, (float)len);
 }
 __global__ void __launch_bounds__(kThreads) k_frame_power_fast(const float2 *__restrict__ frames, float *__restrict__ power,
                                                                long n_frames, int len)
