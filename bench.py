@@ -335,6 +335,8 @@ def run_gpu(args):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("k_stream_rx2_exact_inject_bytes_per_launch")
+                if traffic is not None and n_frames != 1_000_000:
+                    traffic = traffic * n_frames / 1_000_000        # captured on the 1 M-frame launch
         ber = [c.bit_errors / max(1, c.bits) for c in resident_counts]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
