@@ -94,6 +94,8 @@ SIGNATURES = {
     "ofdm_multipath_taps": (_I, [_VP, _VP, _VP, _I, _VP, _L, _I]),
     "ofdm_multipath_philox": (_I, [_VP, _VP, _U32, _U64, _I, _VP, _VP, _L, _I]),
     "ofdm_mc_sweep_multipath_dev": (_I, [_VP, _U32, _U64, _L, _I, _I, _VP, _I, _I, _VP]),
+    "ofdm_counters_pack": (_I, [_VP, _VP, _I, _VP, _VP]),
+    "ofdm_counters_unpack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_finalize": (_I, [C.POINTER(Counters), C.POINTER(_F)]),
     "ofdm_write_float_array_to_file": (_I, [_VP, _I, C.c_char_p]),
     "ofdm_write_complex_array_to_file": (_I, [_VP, _I, C.c_char_p, _I]),

@@ -782,6 +782,25 @@ int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, l
     return OFDM_OK;
 }
 
+int ofdm_counters_pack(ofdm_ctx *ctx, const ofdm_counters *counters, int n, uint64_t *ints, double *dbls)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0);
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, counters != nullptr && ints != nullptr && dbls != nullptr);
+    k_counters_pack<<<blocks_1d(n), 256, 0, ctx->stream>>>(counters, n, reinterpret_cast<unsigned long long *>(ints), dbls);
+    return check_launch(ctx, "k_counters_pack");
+}
+int ofdm_counters_unpack(ofdm_ctx *ctx, ofdm_counters *counters, int n, const uint64_t *ints, const double *dbls)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0);
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, counters != nullptr && ints != nullptr && dbls != nullptr);
+    k_counters_unpack<<<blocks_1d(n), 256, 0, ctx->stream>>>(counters, n, reinterpret_cast<const unsigned long long *>(ints), dbls);
+    return check_launch(ctx, "k_counters_unpack");
+}
+
 int ofdm_counters_finalize(const ofdm_counters *c, float res[3])
 {
     if (!c || !res) return OFDM_ERR_INVALID;

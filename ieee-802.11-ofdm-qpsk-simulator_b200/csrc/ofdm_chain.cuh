@@ -526,4 +526,23 @@ __global__ void __launch_bounds__(kThreads) k_multipath(const float2 *__restrict
     }
 }
 
+// ofdm_counters is 5 x u64 + 3 x double per SNR point; collectives want homogeneous buffers
+__global__ void k_counters_pack(const ofdm_counters *__restrict__ c, int n, unsigned long long *__restrict__ ints, double *__restrict__ dbls)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ofdm_counters v = c[i];
+    ints[5 * i] = v.bit_errors; ints[5 * i + 1] = v.bits; ints[5 * i + 2] = v.frames_in_error; ints[5 * i + 3] = v.rail_errors; ints[5 * i + 4] = v.frames;
+    dbls[3 * i] = v.sum_err2; dbls[3 * i + 1] = v.sum_ref2; dbls[3 * i + 2] = v.sum_evm_lin;
+}
+__global__ void k_counters_unpack(ofdm_counters *__restrict__ c, int n, const unsigned long long *__restrict__ ints, const double *__restrict__ dbls)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ofdm_counters v;
+    v.bit_errors = ints[5 * i]; v.bits = ints[5 * i + 1]; v.frames_in_error = ints[5 * i + 2]; v.rail_errors = ints[5 * i + 3]; v.frames = ints[5 * i + 4];
+    v.sum_err2 = dbls[3 * i]; v.sum_ref2 = dbls[3 * i + 1]; v.sum_evm_lin = dbls[3 * i + 2];
+    c[i] = v;
+}
+
 }  // namespace ofdm

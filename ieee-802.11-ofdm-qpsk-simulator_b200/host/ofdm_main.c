@@ -12,6 +12,9 @@
  *       MSB-first ASCII bits, space-padded to a multiple of 96 bits), one frame, prints the received
  *       message per SNR point like Receiver() does (OFDM.c:1169-1182);
  *   --frames N (N > 1): N frames of Philox random bits per SNR point through the fused Monte-Carlo kernel.
+ *   --gpus N: the frames of the Monte-Carlo sweep are sharded across N GPUs of this node by global frame index
+ *       (one context per GPU, all driven from this thread) and the counters are summed with ONE NCCL all-reduce
+ *       per buffer type (built with -DOFDM_WITH_NCCL; link -lnccl).
  * There is no CPU fallback: without a CUDA device the program exits with an error.
  */
 #include <math.h>
@@ -20,6 +23,9 @@
 #include <string.h>
 
 #include "ofdm_b200.h"
+#ifdef OFDM_WITH_NCCL
+#include <nccl.h>
+#endif
 
 #define CHECK(call)                                                                                  \
     do {                                                                                             \
@@ -64,12 +70,67 @@ static void decode_message(const uint32_t *words, int n_bits, char *out)
     out[n_bits / 8] = 0;
 }
 
+#ifdef OFDM_WITH_NCCL
+#define NCHECK(call)                                                                   \
+    do {                                                                               \
+        ncclResult_t r_ = (call);                                                      \
+        if (r_ != ncclSuccess) { fprintf(stderr, "%s failed: %s\n", #call, ncclGetErrorString(r_)); return 1; } \
+    } while (0)
+
+/* shard (frame range) across GPUs, counter-based RNG keyed on the global frame index, one all-reduce */
+static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, const float *SNR, int n_snr, int mode, ofdm_counters *totals)
+{
+    ofdm_ctx *ctxs[8] = {0};
+    ofdm_ctx *ctx = NULL;
+    void *cnt[8], *ints[8], *dbls[8];
+    ncclComm_t comms[8];
+    int devs[8];
+    if (n_gpus < 1 || n_gpus > 8) { fprintf(stderr, "--gpus must be 1..8\n"); return 2; }
+    for (int d = 0; d < n_gpus; ++d) {
+        devs[d] = d;
+        CHECK(ofdm_ctx_create(&ctxs[d], d));
+        ctx = ctxs[d];
+        CHECK(ofdm_dev_alloc(ctx, &cnt[d], sizeof(ofdm_counters) * (size_t)n_snr));
+        CHECK(ofdm_dev_alloc(ctx, &ints[d], sizeof(uint64_t) * 5 * (size_t)n_snr));
+        CHECK(ofdm_dev_alloc(ctx, &dbls[d], sizeof(double) * 3 * (size_t)n_snr));
+        CHECK(ofdm_memset_dev(ctx, cnt[d], 0, sizeof(ofdm_counters) * (size_t)n_snr));
+    }
+    NCHECK(ncclCommInitAll(comms, n_gpus, devs));
+    for (int d = 0; d < n_gpus; ++d) {                      /* all GPUs run their shard concurrently (async launches) */
+        long base = frames / n_gpus, rem = frames % n_gpus;
+        long lo = d * base + (d < rem ? d : rem), n = base + (d < rem ? 1 : 0);
+        ctx = ctxs[d];
+        CHECK(ofdm_mc_sweep_philox_dev(ctx, seed, (uint64_t)lo, n, n_sym, SNR, n_snr, mode, (ofdm_counters *)cnt[d]));
+        CHECK(ofdm_counters_pack(ctx, (const ofdm_counters *)cnt[d], n_snr, (uint64_t *)ints[d], (double *)dbls[d]));
+    }
+    NCHECK(ncclGroupStart());
+    for (int d = 0; d < n_gpus; ++d) {
+        NCHECK(ncclAllReduce(ints[d], ints[d], 5 * (size_t)n_snr, ncclUint64, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+        NCHECK(ncclAllReduce(dbls[d], dbls[d], 3 * (size_t)n_snr, ncclDouble, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+    }
+    NCHECK(ncclGroupEnd());
+    for (int d = 0; d < n_gpus; ++d) {
+        ctx = ctxs[d];
+        CHECK(ofdm_counters_unpack(ctx, (ofdm_counters *)cnt[d], n_snr, (const uint64_t *)ints[d], (const double *)dbls[d]));
+    }
+    ctx = ctxs[0];
+    CHECK(ofdm_memcpy_d2h(ctx, totals, cnt[0], sizeof(ofdm_counters) * (size_t)n_snr));
+    for (int d = 0; d < n_gpus; ++d) { ctx = ctxs[d]; CHECK(ofdm_ctx_sync(ctx)); }
+    for (int d = 0; d < n_gpus; ++d) {
+        ncclCommDestroy(comms[d]);
+        ofdm_dev_free(ctxs[d], cnt[d]); ofdm_dev_free(ctxs[d], ints[d]); ofdm_dev_free(ctxs[d], dbls[d]);
+        ofdm_ctx_destroy(ctxs[d]);
+    }
+    return 0;
+}
+#endif
+
 int main(int argc, char **argv)
 {
     const char *message = "Hey! I am Vivaswan";          /* OFDM.c:20 */
     const char *outdir = "data", *dump = NULL;
     long frames = 1;
-    int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0;
+    int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0, n_gpus = 1;
     float snr_start = 6.0f, snr_step = 1.0f;             /* OFDM.c:18, :1195-1198 */
     unsigned seed = 1;
     for (int i = 1; i < argc; ++i) {
@@ -84,6 +145,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--snr-count")) n_snr = atoi(v);
         else if (!strcmp(a, "--seed")) seed = (unsigned)strtoul(v, NULL, 10);
         else if (!strcmp(a, "--device")) device = atoi(v);
+        else if (!strcmp(a, "--gpus")) n_gpus = atoi(v);
         else if (!strcmp(a, "--outdir")) outdir = v;
         else if (!strcmp(a, "--dump")) dump = v;
         else if (!strcmp(a, "--mode")) mode = !strcmp(v, "fast") ? OFDM_MODE_FAST : OFDM_MODE_EXACT;
@@ -93,13 +155,25 @@ int main(int argc, char **argv)
     if (n_snr < 1 || n_snr > 64 || frames < 1) { fprintf(stderr, "need 1 <= snr-count <= 64 and frames >= 1\n"); return 2; }
 
     ofdm_ctx *ctx = NULL;
-    CHECK(ofdm_ctx_create(&ctx, device));
-
     float SNR[64], EVM_dB[64], EVM_AGC_dB[64], BER[64];
     for (int i = 0; i < n_snr; ++i) SNR[i] = snr_start + snr_step * (float)i;
     ofdm_counters totals[64];
 
-    if (frames > 1) {
+    if (n_gpus > 1) {
+#ifdef OFDM_WITH_NCCL
+        if (frames < 2) { fprintf(stderr, "--gpus needs --frames N > 1\n"); return 2; }
+        int rc = sweep_multi_gpu(n_gpus, seed, frames, n_sym, SNR, n_snr, mode, totals);
+        if (rc) return rc;
+#else
+        fprintf(stderr, "built without NCCL (make ofdm_sweep NCCL=1)\n");
+        return 2;
+#endif
+    }
+    if (n_gpus <= 1) CHECK(ofdm_ctx_create(&ctx, device));
+
+    if (n_gpus > 1) {
+        /* totals already hold the all-reduced counters */
+    } else if (frames > 1) {
         CHECK(ofdm_mc_sweep_philox(ctx, seed, 0, frames, n_sym, SNR, n_snr, mode, totals));
     } else {
         uint8_t *bits = NULL;
@@ -160,6 +234,6 @@ int main(int argc, char **argv)
     snprintf(path, sizeof path, "%s/Output_EVM_AGC_DB.txt", outdir);  CHECK(ofdm_write_float_array_to_file(EVM_AGC_dB, n_snr, path));
     snprintf(path, sizeof path, "%s/Output_BER.txt", outdir);         CHECK(ofdm_write_float_array_to_file(BER, n_snr, path));
     if (!quiet) printf("\nCode Run Successful!\n");
-    ofdm_ctx_destroy(ctx);
+    if (ctx) ofdm_ctx_destroy(ctx);
     return 0;
 }

@@ -186,6 +186,12 @@ int ofdm_multipath_philox(ofdm_ctx *ctx, const float *tx_dev, uint32_t seed, uin
 int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps,
                                 const float *snr_db, int n_snr, int mode, ofdm_counters *counters_dev);
 
+/* Multi-GPU glue: split device counters [n] into homogeneous buffers (ints [n][5] uint64: bit_errors, bits,
+ * frames_in_error, rail_errors, frames; dbls [n][3]: sum_err2, sum_ref2, sum_evm_lin) for a sum all-reduce
+ * (ncclUint64 / ncclDouble), and merge them back.  The all-reduce is the path's only exchange. */
+int ofdm_counters_pack(ofdm_ctx *ctx, const ofdm_counters *counters_dev, int n, uint64_t *ints_dev, double *dbls_dev);
+int ofdm_counters_unpack(ofdm_ctx *ctx, ofdm_counters *counters_dev, int n, const uint64_t *ints_dev, const double *dbls_dev);
+
 /* Res[3] = {EVM_dB, EVM_AGC_dB, BER} of OFDM.c:1163-1165 from batch totals */
 int ofdm_counters_finalize(const ofdm_counters *c, float res[3]);
 

@@ -131,3 +131,21 @@ def test_c_host_driver_writes_reference_format(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     ber = [float(w) for w in open(out / "Output_BER.txt").read().split()]
     assert len(ber) == 11 and abs(ber[0] - 0.261) < 0.003 and abs(ber[5] - 1.75e-3) < 2e-4 and ber[-1] == 0.0
+
+
+def test_c_host_driver_multi_gpu_nccl(tmp_path):
+    """--gpus N: frames sharded by global index + one NCCL all-reduce per buffer type; the result files must be
+    byte-identical to the single-GPU run (integer totals are split-invariant, EXACT mode)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "ieee-802.11-ofdm-qpsk-simulator_b200", "ofdm_sweep")
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("data%d" % gpus)
+        out.mkdir()
+        r = subprocess.run([exe, "--quiet", "--outdir", str(out), "--gpus", str(gpus), "--frames", "300001", "--snr-start", "0",
+                            "--snr-count", "9", "--snr-step", "2"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append({n: open(out / n).read() for n in ("Output_BER.txt", "Output_EVM_AGC_DB.txt", "Output_SNR.txt")})
+    assert outs[0] == outs[1]
