@@ -94,6 +94,9 @@ SIGNATURES = {
     "ofdm_multipath_taps": (_I, [_VP, _VP, _VP, _I, _VP, _L, _I]),
     "ofdm_multipath_philox": (_I, [_VP, _VP, _U32, _U64, _I, _VP, _VP, _L, _I]),
     "ofdm_mc_sweep_multipath_dev": (_I, [_VP, _U32, _U64, _L, _I, _I, _VP, _I, _I, _VP]),
+    "ofdm_rrc_tx": (_I, [_VP, _VP, _VP, _L, _I]),
+    "ofdm_rrc_rx": (_I, [_VP, _VP, _VP, _L, _I, _I, _I]),
+    "ofdm_awgn_inject_len": (_I, [_VP, _VP, _VP, _VP, _F, _VP, _L, _I, _I]),
     "ofdm_counters_pack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_unpack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_finalize": (_I, [C.POINTER(Counters), C.POINTER(_F)]),
@@ -357,6 +360,23 @@ class Ofdm:
         self._check(self.lib.ofdm_mc_sweep_multipath_dev(self.h, seed, frame0, n_frames, n_sym, n_taps, snr.ctypes.data, len(snr), mode,
                                                          _ptr(cnt)))
         return None if counters is not None else self.read_counters(cnt)
+
+    def rrc_tx(self, frames):
+        n, length = frames.shape[0], frames.shape[1]
+        out = self.empty((n, 2 * length + 20, 2), self.torch.float32)
+        self._check(self.lib.ofdm_rrc_tx(self.h, _ptr(frames), _ptr(out), n, length))
+        return out
+
+    def rrc_rx(self, x, packet_idx, frame_len_):
+        n, in_len = x.shape[0], x.shape[1]
+        out = self.empty((n, frame_len_, 2), self.torch.float32)
+        self._check(self.lib.ofdm_rrc_rx(self.h, _ptr(x), _ptr(out), n, in_len, packet_idx, frame_len_))
+        return out
+
+    def awgn_inject_len(self, tx, g, snr_db, mode, power=None):
+        ota = self.empty(tuple(tx.shape), self.torch.float32)
+        self._check(self.lib.ofdm_awgn_inject_len(self.h, _ptr(tx), _ptr(g), _ptr(power), snr_db, _ptr(ota), tx.shape[0], tx.shape[1], mode))
+        return ota
 
     def finalize(self, counters):
         res = (_F * 3)()

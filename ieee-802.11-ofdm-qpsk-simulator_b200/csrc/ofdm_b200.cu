@@ -782,6 +782,56 @@ int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, l
     return OFDM_OK;
 }
 
+// ------------------------------------------------------------------ pulse shaping
+int ofdm_rrc_tx(ofdm_ctx *ctx, const float *frames, float *out, long n_frames, int frame_len)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= OFDM_FRAME_LEN(OFDM_MAX_SYM));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, frames != nullptr && out != nullptr && frames != out);
+    const size_t smem = (size_t)kWarpsPerBlock * frame_len * sizeof(float2);
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_tx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = grid_for(ctx, k_rrc_tx, smem, kWarpsPerBlock, n_frames);
+    k_rrc_tx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), reinterpret_cast<float2 *>(out), n_frames, frame_len);
+    return check_launch(ctx, "k_rrc_tx");
+}
+int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in, float *out, long n_frames, int in_len, int packet_idx, int frame_len)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && in_len >= 1 && in_len <= 2 * OFDM_FRAME_LEN(OFDM_MAX_SYM) + 64 && frame_len >= 1 && packet_idx >= 0);
+    // the reference reads Rx_filter_signal[packet_idx + 2*(frame_len-1)] (:992-994): it must exist (in_len + 20 filtered samples)
+    OFDM_REQUIRE(ctx, (long)packet_idx + 2L * (frame_len - 1) < (long)in_len + 20);
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && in != out);
+    const size_t smem = (size_t)kWarpsPerBlock * in_len * sizeof(float2);
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = grid_for(ctx, k_rrc_rx, smem, kWarpsPerBlock, n_frames);
+    k_rrc_rx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), n_frames, in_len,
+                                                   packet_idx, frame_len);
+    return check_launch(ctx, "k_rrc_rx");
+}
+int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx, const float *g, const float *power, float snr_db, float *ota, long n_frames,
+                         int frame_len, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= 2 * OFDM_FRAME_LEN(OFDM_MAX_SYM) + 64 && mode_ok(mode));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, tx != nullptr && ota != nullptr && g != nullptr);
+    const float *pw = nullptr;
+    if (int st = resolve_power(ctx, tx, power, n_frames, frame_len, mode, &pw)) return st;
+    const float2 *x = reinterpret_cast<const float2 *>(tx);
+    float2 *y = reinterpret_cast<float2 *>(ota);
+    const float sl = snr_linear(snr_db);
+    if (mode == OFDM_MODE_EXACT) {
+        int grid = grid_for(ctx, k_awgn<true, kNoiseInject>, 0, kWarpsPerBlock, n_frames);
+        k_awgn<true, kNoiseInject><<<grid, kThreads, 0, ctx->stream>>>(x, g, pw, sl, 0, 0, 0, y, n_frames, frame_len);
+    } else {
+        int grid = grid_for(ctx, k_awgn<false, kNoiseInject>, 0, kWarpsPerBlock, n_frames);
+        k_awgn<false, kNoiseInject><<<grid, kThreads, 0, ctx->stream>>>(x, g, pw, sl, 0, 0, 0, y, n_frames, frame_len);
+    }
+    return check_launch(ctx, "k_awgn");
+}
+
 int ofdm_counters_pack(ofdm_ctx *ctx, const ofdm_counters *counters, int n, uint64_t *ints, double *dbls)
 {
     if (int st = bind(ctx)) return st;

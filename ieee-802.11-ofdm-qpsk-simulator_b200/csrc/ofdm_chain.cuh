@@ -545,4 +545,63 @@ __global__ void k_counters_unpack(ofdm_counters *__restrict__ c, int n, const un
     c[i] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// pulse shaping.  x2 zero-stuff + 21-tap RRC on the way out (OFDM.c:587-605), matched filter +
+// decimation on the way in (OFDM.c:959-996), both as the reference's Convolution() (:342-364) accumulates them:
+// float, input index ascending, real taps (RRC_Filter_Tx :32) so each product is (a*h, b*h).  Zero-stuffed inputs
+// contribute exact zeros and are skipped.  One warp per frame, frame staged in shared memory, coalesced stores.
+__constant__ float c_rrc[21] = {-0.000454720514876223f, 0.00353689555574986f, -0.00714560809091226f, 0.00757906190517828f,
+                                0.00214368242727367f, -0.0106106866672496f, 0.0300115539818315f, -0.0530534333362480f,
+                                -0.0750288849545787f, 0.409168714634052f, 0.803738600397980f, 0.409168714634052f,
+                                -0.0750288849545787f, -0.0530534333362480f, 0.0300115539818315f, -0.0106106866672496f,
+                                0.00214368242727367f, 0.00757906190517828f, -0.00714560809091226f, 0.00353689555574986f,
+                                -0.000454720514876223f};
+
+__global__ void __launch_bounds__(kThreads) k_rrc_tx(const float2 *__restrict__ frames, float2 *__restrict__ out, long n_frames, int len)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * len;
+    const int n_out = 2 * len + 20;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        for (int i = lane; i < len; i += 32) sx[i] = frames[f * len + i];
+        __syncwarp();
+        for (int k = lane; k < n_out; k += 32) {
+            const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < 2 * len - 1 ? k : 2 * len - 1;
+            float ar = 0.f, ai = 0.f;
+            for (int i = lo + (lo & 1); i <= hi; i += 2) {                  // even (non-stuffed) inputs, ascending
+                const float2 a = sx[i >> 1];
+                const float h = c_rrc[k - i];
+                ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
+            }
+            out[f * n_out + k] = make_float2(ar, ai);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_rrc_rx(const float2 *__restrict__ in, float2 *__restrict__ out, long n_frames, int in_len,
+                                                     int packet_idx, int frame_len)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * in_len;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        for (int i = lane; i < in_len; i += 32) sx[i] = in[f * in_len + i];
+        __syncwarp();
+        for (int r = lane; r < frame_len; r += 32) {
+            const int k = packet_idx + 2 * r;                               // :992-996
+            const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < in_len - 1 ? k : in_len - 1;
+            float ar = 0.f, ai = 0.f;
+            for (int i = lo; i <= hi; ++i) {
+                const float2 a = sx[i];
+                const float h = c_rrc[k - i];
+                ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
+            }
+            out[f * frame_len + r] = make_float2(ar, ai);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace ofdm

@@ -186,6 +186,18 @@ int ofdm_multipath_philox(ofdm_ctx *ctx, const float *tx_dev, uint32_t seed, uin
 int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps,
                                 const float *snr_db, int n_snr, int mode, ofdm_counters *counters_dev);
 
+/* ---- pulse shaping (the blocks either side of the stage chain on the wire) ----
+ * ofdm_rrc_tx: x2 zero-stuff + 21-tap RRC (RRC_Filter_Tx, OFDM.c:32) full convolution, OFDM.c:587-605 with Convolution()
+ *   OFDM.c:342-364: [n_frames][frame_len] -> [n_frames][2*frame_len + 20].
+ * ofdm_rrc_rx: matched filter + decimation, OFDM.c:959-996: full convolution of in_len samples, then every 2nd sample
+ *   from packet_idx, frame_len of them.  packet_idx = 20 re-aligns a frame shaped by ofdm_rrc_tx (the reference finds
+ *   it with Packet_Detection/Packet_Selection, which are not part of this library yet).
+ * ofdm_awgn_inject_len: Transmission_Over_Air (OFDM.c:635) on frames of any length, e.g. the oversampled waveform. */
+int ofdm_rrc_tx(ofdm_ctx *ctx, const float *frames_dev, float *out_dev, long n_frames, int frame_len);
+int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in_dev, float *out_dev, long n_frames, int in_len, int packet_idx, int frame_len);
+int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx_dev, const float *g_dev, const float *power_dev, float snr_db,
+                         float *ota_dev, long n_frames, int frame_len, int mode);
+
 /* Multi-GPU glue: split device counters [n] into homogeneous buffers (ints [n][5] uint64: bit_errors, bits,
  * frames_in_error, rail_errors, frames; dbls [n][3]: sum_err2, sum_ref2, sum_evm_lin) for a sum all-reduce
  * (ncclUint64 / ncclDouble), and merge them back.  The all-reduce is the path's only exchange. */

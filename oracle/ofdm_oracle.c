@@ -458,3 +458,42 @@ void orc_chain_multipath(const uint8_t *bits, const float *g, const float *taps,
     }
     free(tx); free(ch); free(ota); free(mod);
 }
+
+/* ---------------- section 8(f) rank 1: x2 oversampling + RRC pulse shaping (OFDM.c:32, 342-364, 587-605, 959-996) ----------------
+ * Convolution() accumulates Out[i+j] += Inp[i]*H[j] in float, i ascending; H is real (imaginary part 0), so each
+ * product is (a*h, b*h) rounded to float.  Per output sample k that is: for i ascending, j = k - i in [0, 20]. */
+static const double rrc_taps_d[21] = {-0.000454720514876223, 0.00353689555574986, -0.00714560809091226, 0.00757906190517828,
+    0.00214368242727367, -0.0106106866672496, 0.0300115539818315, -0.0530534333362480, -0.0750288849545787, 0.409168714634052,
+    0.803738600397980, 0.409168714634052, -0.0750288849545787, -0.0530534333362480, 0.0300115539818315, -0.0106106866672496,
+    0.00214368242727367, 0.00757906190517828, -0.00714560809091226, 0.00353689555574986, -0.000454720514876223};   /* RRC_Filter_Tx :32 */
+
+void orc_rrc_taps(float *out21) { for (int i = 0; i < 21; ++i) out21[i] = (float)rrc_taps_d[i]; }
+
+static void conv21(const cf32 *in, int n_in, cf32 *out)
+{
+    float h[21];
+    orc_rrc_taps(h);
+    for (int k = 0; k < n_in + 20; ++k) {
+        float ar = 0.0f, ai = 0.0f;
+        int lo = k - 20 < 0 ? 0 : k - 20, hi = k < n_in - 1 ? k : n_in - 1;
+        for (int i = lo; i <= hi; ++i) { ar += in[i].re * h[k - i]; ai += in[i].im * h[k - i]; }
+        out[k].re = ar; out[k].im = ai;
+    }
+}
+void orc_rrc_tx(const float *frame, int len, float *out)
+{
+    const cf32 *x = (const cf32 *)frame;
+    cf32 *up = (cf32 *)calloc((size_t)(2 * len), sizeof(cf32));
+    for (int i = 0; i < len; ++i) up[2 * i] = x[i];
+    conv21(up, 2 * len, (cf32 *)out);
+    free(up);
+}
+void orc_rrc_rx(const float *in, int in_len, int packet_idx, int frame_len, float *out)
+{
+    cf32 *f = (cf32 *)malloc(sizeof(cf32) * (size_t)(in_len + 20));
+    conv21((const cf32 *)in, in_len, f);
+    cf32 *r = (cf32 *)out;
+    int index = 0;
+    for (int i = packet_idx; i < 2 * frame_len + packet_idx - 1; i += 2) r[index++] = f[i];
+    free(f);
+}

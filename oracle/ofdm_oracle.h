@@ -52,4 +52,7 @@ void  orc_philox_taps(uint32_t seed, uint64_t frame0, long n_frames, int n_taps,
 void  orc_apply_taps(const float *tx, const float *taps, int n_taps, float *out, int len);
 void  orc_chain_multipath(const uint8_t *bits, const float *g, const float *taps, int n_taps, long n_frames,
                           int n_sym, float snr_db, orc_counters *acc, int *frame_bit_errors, float *frame_evm_lin);
+void  orc_rrc_taps(float *out21);
+void  orc_rrc_tx(const float *frame, int len, float *out /* (2*len+20)*2 */);
+void  orc_rrc_rx(const float *in, int in_len, int packet_idx, int frame_len, float *out /* frame_len*2 */);
 #endif

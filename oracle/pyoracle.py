@@ -144,6 +144,27 @@ class _Base:
                 res[k][i] = getattr(st, k)
         return res
 
+    def rrc_taps(self):
+        t = np.zeros(21, np.float32)
+        self._f("rrc_taps")(_p(t))
+        return t
+
+    def rrc_tx(self, frames):
+        frames = _f32(frames)
+        fr = frames.reshape(-1, frames.shape[-2], 2)
+        out = np.zeros((fr.shape[0], 2 * fr.shape[1] + 20, 2), np.float32)
+        for i in range(fr.shape[0]):
+            self._f("rrc_tx")(_p(fr[i]), C.c_int(fr.shape[1]), _p(out[i]))
+        return out
+
+    def rrc_rx(self, x, packet_idx, frame_len):
+        x = _f32(x)
+        xr = x.reshape(-1, x.shape[-2], 2)
+        out = np.zeros((xr.shape[0], frame_len, 2), np.float32)
+        for i in range(xr.shape[0]):
+            self._f("rrc_rx")(_p(xr[i]), C.c_int(xr.shape[1]), C.c_int(packet_idx), C.c_int(frame_len), _p(out[i]))
+        return out
+
     def chain(self, bits, g, n_sym, snr_db, noise_mode=0, per_frame=False):
         bits = _u8(bits).reshape(-1, 96 * n_sym)
         n = bits.shape[0]

@@ -394,3 +394,36 @@ void ref_write_float(const float *a, int n, const char *fname)
 {
     write_float_array_to_file((float *)a, n, (char *)fname);
 }
+
+/* ---- section 8(f) rank 1: pulse shaping, composed from the reference's own Convolution() (:342) ----
+ * TX (:587-605): x2 zero-stuff, full convolution with RRC_Filter_Tx (21 taps) -> 2*len + 20 samples.
+ * RX (:959-996): full convolution of the captured samples with the same filter, then every 2nd sample
+ * from packet_idx, frame_len of them (:986-996 with Data_Frame_Size = frame_len). */
+void ref_rrc_tx(const float *frame, int len, float *out /* (2*len+20)*2 */)
+{
+    float complex *x = Allocate_Array_1D(len), *up = Allocate_Array_1D(2 * len);
+    get(x, frame, len);
+    for (int i = 0; i < len; ++i) { up[2*i] = x[i]; up[2*i + 1] = 0; }          /* :591-595 */
+    hush();
+    float complex *y = Convolution(up, RRC_Filter_Tx, 2 * len, len_RRC_Coeff);   /* :605 */
+    unhush();
+    put(out, y, 2 * len + len_RRC_Coeff - 1);
+    free(x); free(up); free(y);
+}
+void ref_rrc_rx(const float *in, int in_len, int packet_idx, int frame_len, float *out /* frame_len*2 */)
+{
+    float complex *x = Allocate_Array_1D(in_len);
+    get(x, in, in_len);
+    hush();
+    float complex *f = Convolution(x, RRC_Filter_Tx, in_len, len_RRC_Coeff);     /* :965 */
+    unhush();
+    float complex *r = Allocate_Array_1D(frame_len);
+    int index = 0;
+    for (int i = packet_idx; i < 2 * frame_len + packet_idx - 1; i += 2) { r[index] = f[i]; index += 1; }   /* :992-996 */
+    put(out, r, frame_len);
+    free(x); free(f); free(r);
+}
+void ref_rrc_taps(float *out21)
+{
+    for (int i = 0; i < 21; ++i) out21[i] = crealf(RRC_Filter_Tx[i]);
+}

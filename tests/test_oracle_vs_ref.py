@@ -111,3 +111,17 @@ def test_degenerate_frames(port, ref):
     for frames in (z, np.zeros_like(tx), tx * np.float32(1e18), tx * np.float32(1e-18)):
         rr, rp = ref.rx_frames(frames, bits, 2), port.rx_frames(frames, bits, 2)
         assert same(rr["bits"], rp["bits"]) and same(rr["bit_errors"], rp["bit_errors"]) and same(rr["eq"], rp["eq"])
+
+
+def test_rrc_pulse_shaping_port_matches_reference(port, ref):
+    """the port's restatement of Convolution()-based shaping equals the reference's."""
+    bits, _ = bits_and_noise(3, 8, 2)
+    tx = ref.tx_frames(bits, 2)
+    assert same(port.rrc_taps(), ref.rrc_taps())
+    shaped = ref.rrc_tx(tx)
+    assert shaped.shape == (8, 660, 2) and same(port.rrc_tx(tx), shaped)
+    noisy = shaped + np.random.default_rng(0).standard_normal(shaped.shape).astype(np.float32) * np.float32(0.05)
+    for idx in (0, 20, 33):
+        assert same(port.rrc_rx(noisy, idx, 320), ref.rrc_rx(noisy, idx, 320))
+    # aligned at the filter-pair delay the chain is recovered up to the RRC pair's residual ISI
+    assert np.max(np.abs(ref.rrc_rx(shaped, 20, 320) - tx)) < 0.04
