@@ -671,7 +671,7 @@ int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long
         McParams p;
         memset(&p, 0, sizeof p);
         p.seed = seed; p.frame0 = frame0; p.n_frames = n_frames; p.n_snr = n_snr; p.counters = counters;
-        for (int i = 0; i < n_snr; ++i) p.snr_lin[i] = snr_linear(snr_db[i]);
+        for (int i = 0; i < n_snr; ++i) { p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i])); }
         const size_t smem = mc_smem_bytes();
         if (mode == OFDM_MODE_EXACT) {
             OFDM_CUDA(ctx, cudaFuncSetAttribute(k_mc_philox<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -56,6 +56,7 @@ struct McParams {
     long n_frames;
     int n_snr;
     float snr_lin[kMaxSnr];         // (float)pow(10, snr/10), OFDM.c:645
+    float inv_sqrt_snr[kMaxSnr];    // 1/sqrt(snr_lin), fast mode's noise scale factor
     ofdm_counters *counters;        // [n_snr], accumulated into
 };
 
@@ -64,8 +65,6 @@ struct WarpShared {
     float2 tile[kWarpTile];         // transform transpose tile, then the F exchange tile (2 x kWin used)
     float2 lts[2][kWin];            // FFT of the two received LTS halves
     float2 body[2][kWin];           // the frame's two symbol bodies in time (skewed windows)
-    uint32_t acc_u[kMaxSnr][4];     // per SNR point: I-rail, Q-rail, both-rail errors, frames in error
-    float acc_f[kMaxSnr][2];        // per SNR point: sum |E-tx|^2, sum of per-frame EVM (flushed to double at the end)
 };
 
 template <bool EXACT>
@@ -86,16 +85,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
     for (int i = 0; i < 8; ++i) dmap_tx[i] = c_tab.bin_data[8 * slot_m<EXACT>(i) + u];
 
     for (int i = threadIdx.x; i < 128; i += kThreads) s_ltsx[(i >> 6) * kWin + (i & 63)] = c_tab.lts_time[32 + i];
-    for (int i = lane; i < kMaxSnr; i += 32) {
-        ws.acc_u[i][0] = ws.acc_u[i][1] = ws.acc_u[i][2] = ws.acc_u[i][3] = 0u;
-        ws.acc_f[i][0] = ws.acc_f[i][1] = 0.f;
-    }
     __syncthreads();
 
     const float2 *src = grp < 2 ? s_ltsx + grp * kWin : ws.body[grp - 2];
     const int blk_base = (grp < 2 ? 8 + 16 * grp : 44 + 20 * (grp - 2)) + u;        // window_block_base(n0) + u
     const double q = (double)kQpsk;
     const float inv_ref2 = (float)(1.0 / (96.0 * (2.0 * q * q)));
+    // Per-SNR totals live in registers: lane L owns SNR points L and L + 32 (n_snr <= 64).  The float EVM sums are
+    // flushed into doubles every 64 frames.
+    uint32_t m_i[2] = {0, 0}, m_q[2] = {0, 0}, m_b[2] = {0, 0}, m_ferr[2] = {0, 0};
+    float m_e2[2] = {0.f, 0.f}, m_evm[2] = {0.f, 0.f};
+    double d_e2[2] = {0.0, 0.0}, d_evm[2] = {0.0, 0.0};
     uint32_t n_done = 0;
 
     for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < p.n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
@@ -103,6 +103,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
         // ---- payload bits (Philox, one block per symbol) and Transmitter :500-565 for the two symbols
         const uint4 b0 = Philox::run(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), 0u, kDomainBits), p.seed, 0u);
         const uint4 b1 = Philox::run(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), 1u, kDomainBits), p.seed, 0u);
+        // the lane's three bit pairs of this frame (constant over the SNR loop)
+        uint32_t txp[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int wsel = ic.word[t];
+            const uint32_t w = wsel == 0 ? b0.x : wsel == 1 ? b0.y : wsel == 2 ? b0.z : wsel == 3 ? b1.x : wsel == 4 ? b1.y : b1.z;
+            txp[t] = w >> ic.shift[t];
+        }
+        float P;
         {
             const bool s1 = (grp & 1) != 0;
             const uint32_t w0 = s1 ? b1.x : b0.x, w1 = s1 ? b1.y : b0.y, w2 = s1 ? b1.z : b0.z;
@@ -127,7 +136,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 pw += (grp >= 2) ? (np >= 48 ? 2.f * e : e) : 0.f;      // the CP repeats samples 48..63
             }
             __syncwarp();
-            float P;
             if (EXACT) {
                 // OFDM.c:637-643 on the 320-sample frame: the LTS prefix is a constant, the 160 data samples follow in order
                 double *terms = s_terms + warp * 160;
@@ -146,78 +154,79 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
                 P = (pw + c_tab.lts_power_sum) * (1.f / 320.f);
             }
-            // ---- SNR loop OFDM.c:1202: channel :635 + receiver :1018-1165 on the frame held in shared memory
-            for (int si = 0; si < p.n_snr; ++si) {
-                double sigma_d = 0.0; float sigma_f;
-                if (EXACT) { sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si])); sigma_f = (float)sigma_d; }
-                else sigma_f = sqrtf(P / p.snr_lin[si]);
-                float za[4], zb[4];
-                philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)blk_base, kDomainNoise, za);
-                philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)(blk_base + 8), kDomainNoise, zb);
-                float2 r[8];
+        }
+        float sqrtP;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sqrtP) : "f"(P));
+        // ---- SNR loop OFDM.c:1202: channel :635 + receiver :1018-1165 on the frame held in shared memory
+        for (int si = 0; si < p.n_snr; ++si) {
+            double sigma_d = 0.0; float sigma_f;
+            if (EXACT) { sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si])); sigma_f = (float)sigma_d; }
+            else sigma_f = sqrtP * p.inv_sqrt_snr[si];
+            float za[4], zb[4];
+            philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)blk_base, kDomainNoise, za);
+            philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)(blk_base + 8), kDomainNoise, zb);
+            float2 r[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int m = slot_m<EXACT>(i);
-                    float2 s = src[u + 8 * m];
-                    s.x = add_noise<EXACT>(s.x, m < 4 ? za[m & 3] : zb[m & 3], sigma_d, sigma_f);
-                    r[i] = s;
-                }
-                fft64<EXACT>(r, tw, tile, u);
-                // exchange: LTS groups publish A / B, data groups publish F (transform tile is free now)
-                float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
+            for (int i = 0; i < 8; ++i) {
+                const int m = slot_m<EXACT>(i);
+                float2 s = src[u + 8 * m];
+                s.x = add_noise<EXACT>(s.x, m < 4 ? za[m & 3] : zb[m & 3], sigma_d, sigma_f);
+                r[i] = s;
+            }
+            fft64<EXACT>(r, tw, tile, u);
+            // exchange: LTS groups publish A / B, data groups publish F (the transform tile is free now)
+            float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[u + 8 * j] = r[j];
-                __syncwarp();
-                float e2 = 0.f;
-                uint32_t pk = 0;
+            for (int j = 0; j < 8; ++j) dst[u + 8 * j] = r[j];
+            __syncwarp();
+            float e2 = 0.f;
+            uint32_t pk = 0;
 #pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
-                    const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));
-                    const int wsel = ic.word[t];
-                    const uint32_t w = wsel == 0 ? b0.x : wsel == 1 ? b0.y : wsel == 2 ? b0.z : wsel == 3 ? b1.x : wsel == 4 ? b1.y : b1.z;
-                    pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], w >> ic.shift[t], e2);
-                }
-                __syncwarp();
+            for (int t = 0; t < 3; ++t) {
+                const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));
+                pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], txp[t], e2);
+            }
+            __syncwarp();
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    pk += __shfl_xor_sync(0xffffffffu, pk, o);
-                    e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-                }
-                // totals of this frame at this SNR point: lanes 0..5 each own one accumulator column
-                const uint32_t ti = pk & 0xFFu, tq = (pk >> 8) & 0xFFu, tb = pk >> 16;
-                if (lane < 4) {
-                    const uint32_t add = lane == 0 ? ti : lane == 1 ? tq : lane == 2 ? tb : (uint32_t)((ti + 2u * tq - 2u * tb) != 0u);
-                    ws.acc_u[si][lane] += add;
-                } else if (lane < 6) {
-                    ws.acc_f[si][lane - 4] += lane == 4 ? e2 : sqrtf(e2 * inv_ref2);
+            for (int o = 16; o > 0; o >>= 1) {
+                pk += __shfl_xor_sync(0xffffffffu, pk, o);
+                e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+            }
+            float evm;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(evm) : "f"(e2 * inv_ref2));                 // :1124
+            if (lane == (si & 31)) {                                   // the lane that owns this SNR point books the frame
+                if (si < 32) {
+                    m_i[0] += pk & 0xFFu; m_q[0] += (pk >> 8) & 0xFFu; m_b[0] += pk >> 16; m_ferr[0] += pk != 0u;
+                    m_e2[0] += e2; m_evm[0] += evm;
+                } else {
+                    m_i[1] += pk & 0xFFu; m_q[1] += (pk >> 8) & 0xFFu; m_b[1] += pk >> 16; m_ferr[1] += pk != 0u;
+                    m_e2[1] += e2; m_evm[1] += evm;
                 }
             }
         }
         n_done += 1;
-        // the float EVM accumulators are flushed to the global double totals often enough to keep ~1e-6 relative accuracy
-        if ((n_done & 63u) == 0u || f + (long)gridDim.x * kWarpsPerBlock >= p.n_frames) {
-            __syncwarp();
-            for (int si = lane; si < p.n_snr; si += 32) {
-                atomicAdd(&p.counters[si].sum_err2, (double)ws.acc_f[si][0]);
-                atomicAdd(&p.counters[si].sum_evm_lin, (double)ws.acc_f[si][1]);
-                ws.acc_f[si][0] = 0.f; ws.acc_f[si][1] = 0.f;
-            }
-            __syncwarp();
+        if ((n_done & 63u) == 0u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { d_e2[h] += (double)m_e2[h]; d_evm[h] += (double)m_evm[h]; m_e2[h] = 0.f; m_evm[h] = 0.f; }
         }
     }
-    __syncwarp();
+    if (n_done == 0) return;
     const double ref2_frame = 96.0 * (2.0 * q * q);
-    for (int si = lane; si < p.n_snr; si += 32) {
-        if (n_done == 0) break;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int si = lane + 32 * h;
+        if (si >= p.n_snr) continue;
         ofdm_counters *o = p.counters + si;
-        const unsigned long long ti = ws.acc_u[si][0], tq = ws.acc_u[si][1], tb = ws.acc_u[si][2];
-        atomicAdd(reinterpret_cast<unsigned long long *>(&o->bit_errors), ti + 2ull * tq - 2ull * tb);
+        const unsigned long long ti = m_i[h], tq = m_q[h], tb = m_b[h];
+        atomicAdd(reinterpret_cast<unsigned long long *>(&o->bit_errors), ti + 2ull * tq - 2ull * tb);     // map of :423-430
         atomicAdd(reinterpret_cast<unsigned long long *>(&o->rail_errors), ti + tq);
-        atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames_in_error), (unsigned long long)ws.acc_u[si][3]);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames_in_error), (unsigned long long)m_ferr[h]);
         atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames), (unsigned long long)n_done);
         atomicAdd(reinterpret_cast<unsigned long long *>(&o->bits), 192ull * n_done);
+        atomicAdd(&o->sum_err2, d_e2[h] + (double)m_e2[h]);
         atomicAdd(&o->sum_ref2, ref2_frame * (double)n_done);
+        atomicAdd(&o->sum_evm_lin, d_evm[h] + (double)m_evm[h]);
     }
 }
 

@@ -252,7 +252,8 @@ __device__ __forceinline__ float2 box_muller(uint32_t r0, uint32_t r1)
 {
     float u1 = fmaf((float)r0, 0x1p-32f, 0x1p-33f);
     float u2 = (float)r1 * 0x1p-32f;
-    float rad = sqrtf(-2.0f * __logf(u1));
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);
     return make_float2(rad * c, rad * s);
