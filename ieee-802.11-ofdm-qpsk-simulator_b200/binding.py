@@ -97,6 +97,8 @@ SIGNATURES = {
     "ofdm_rrc_tx": (_I, [_VP, _VP, _VP, _L, _I]),
     "ofdm_rrc_rx": (_I, [_VP, _VP, _VP, _L, _I, _I, _I]),
     "ofdm_awgn_inject_len": (_I, [_VP, _VP, _VP, _VP, _F, _VP, _L, _I, _I]),
+    "ofdm_packet_detect": (_I, [_VP, _VP, _VP, _L, _I]),
+    "ofdm_packet_select": (_I, [_VP, _VP, _VP, _L, _I]),
     "ofdm_counters_pack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_unpack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_finalize": (_I, [C.POINTER(Counters), C.POINTER(_F)]),
@@ -377,6 +379,17 @@ class Ofdm:
         ota = self.empty(tuple(tx.shape), self.torch.float32)
         self._check(self.lib.ofdm_awgn_inject_len(self.h, _ptr(tx), _ptr(g), _ptr(power), snr_db, _ptr(ota), tx.shape[0], tx.shape[1], mode))
         return ota
+
+    def packet_detect(self, rx):
+        n, length = rx.shape[0], rx.shape[1]
+        corr = self.empty((n, length - 47), self.torch.float32)
+        self._check(self.lib.ofdm_packet_detect(self.h, _ptr(rx), _ptr(corr), n, length))
+        return corr
+
+    def packet_select(self, corr):
+        idx = self.empty((corr.shape[0],), self.torch.int32)
+        self._check(self.lib.ofdm_packet_select(self.h, _ptr(corr), _ptr(idx), corr.shape[0], corr.shape[1]))
+        return idx
 
     def finalize(self, counters):
         res = (_F * 3)()

@@ -832,6 +832,30 @@ int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx, const float *g, const f
     return check_launch(ctx, "k_awgn");
 }
 
+// ------------------------------------------------------------------ packet detection / selection
+int ofdm_packet_detect(ofdm_ctx *ctx, const float *rx, float *corr, long n, int len)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0 && len >= 48 && len <= 12000);
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, rx != nullptr && corr != nullptr);
+    const size_t smem = (size_t)len * (sizeof(double) + sizeof(float2));
+    OFDM_CUDA(ctx, cudaFuncSetAttribute(k_packet_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long full = (long)ctx->sm_count * 2;
+    int grid = (int)(n < full ? n : full);
+    k_packet_detect<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(rx), corr, n, len);
+    return check_launch(ctx, "k_packet_detect");
+}
+int ofdm_packet_select(ofdm_ctx *ctx, const float *corr, int32_t *idx, long n, int len_corr)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0 && len_corr >= 1);
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, corr != nullptr && idx != nullptr);
+    k_packet_select<<<blocks_1d(n), 256, 0, ctx->stream>>>(corr, idx, n, len_corr);
+    return check_launch(ctx, "k_packet_select");
+}
+
 int ofdm_counters_pack(ofdm_ctx *ctx, const ofdm_counters *counters, int n, uint64_t *ints, double *dbls)
 {
     if (int st = bind(ctx)) return st;

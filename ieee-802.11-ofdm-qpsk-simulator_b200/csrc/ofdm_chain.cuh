@@ -613,4 +613,66 @@ __global__ void __launch_bounds__(kThreads) k_rrc_rx(const float2 *__restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// packet detection and selection (OFDM.c:659-771), batched over captures.
+// Detection: delay 16, window 32, NO conjugate (as the reference and its MATLAB model).  Per lag i the reference
+// accumulates 32 float complex products sequentially and a float "peak" fed with double cabs()^2 terms, then
+// out_i = (float)(cabs(corr)^2 / (double)(float)(peak*peak)); the sequential float sums differ per lag, so there is
+// no sliding-window reuse if the bits are to match.  One block per capture: samples and their |.|^2 terms (glibc
+// hypot, once per sample) staged in shared memory, one lag per thread.
+__global__ void __launch_bounds__(kThreads) k_packet_detect(const float2 *__restrict__ rx, float *__restrict__ corr, long n, int len)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double *pk2 = reinterpret_cast<double *>(s_raw);
+    float2 *sx = reinterpret_cast<float2 *>(pk2 + len);
+    const int n_corr = len - 47;
+    for (long c = blockIdx.x; c < n; c += gridDim.x) {
+        for (int i = threadIdx.x; i < len; i += kThreads) {
+            const float2 v = rx[c * len + i];
+            sx[i] = v;
+            const double h = hypot_glibc((double)v.x, (double)v.y);          // cabs :675
+            pk2[i] = __dmul_rn(h, h);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_corr; i += kThreads) {
+            float cr = 0.f, ci = 0.f, peak = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const float2 a = sx[i + k], b = sx[i + k + 16];
+                cr = __fadd_rn(cr, __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)));      // :674
+                ci = __fadd_rn(ci, __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+                peak = __double2float_rn(__dadd_rn((double)peak, pk2[i + k + 16]));           // :675
+            }
+            const double hc = hypot_glibc((double)cr, (double)ci);
+            corr[c * n_corr + i] = __double2float_rn(__ddiv_rn(__dmul_rn(hc, hc), (double)__fmul_rn(peak, peak)));   // :677
+        }
+        __syncthreads();
+    }
+}
+
+// Selection OFDM.c:685-771: indices above 0.75; a gap > 300 to the previous one opens a candidate; all candidates but
+// the last are tried in order and the first whose correlation 230 lags later is still above the threshold wins:
+// packet_idx = candidate + len_RRC_rx + 1 (= +11); 0 if none.  One thread per capture (the scan is sequential).
+__global__ void k_packet_select(const float *__restrict__ corr, int32_t *__restrict__ idx_out, long n, int len_corr)
+{
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const float *x = corr + c * len_corr;
+    int n_fronts = 0, prev = -1;
+    for (int i = 0; i < len_corr; ++i)
+        if (fabsf(x[i]) > 0.75f) { if (i - prev > 300) ++n_fronts; prev = i; }
+    int result = 0, fronts = 0;
+    prev = -1;
+    for (int i = 0; i < len_corr && result == 0; ++i) {
+        if (!(fabsf(x[i]) > 0.75f)) continue;
+        const bool front = i - prev > 300;
+        prev = i;
+        if (!front) continue;
+        if (++fronts > n_fronts - 1) break;                                  // x < packet_front_count - 1  (:754)
+        const int look = i + 230;                                            // :756 (unchecked in the reference)
+        if (look < len_corr && fabsf(x[look]) > 0.75f) result = i + 11;      // :758
+    }
+    idx_out[c] = result;
+}
+
 }  // namespace ofdm

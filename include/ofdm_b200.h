@@ -198,6 +198,15 @@ int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in_dev, float *out_dev, long n_frame
 int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx_dev, const float *g_dev, const float *power_dev, float snr_db,
                          float *ota_dev, long n_frames, int frame_len, int mode);
 
+/* ---- packet detection / selection, batched over n captures of len samples ----
+ * ofdm_packet_detect: Packet_Detection, OFDM.c:659-683 (delay 16, window 32, no conjugate): corr_dev [n][len-47],
+ *   the real part the reference stores in Corr_Out (its imaginary part is always 0).
+ * ofdm_packet_select: Packet_Selection, OFDM.c:685-771: idx_dev [n] = packet index (candidate + 11), 0 when detection
+ *   fails, as the reference.  The reference reads Corr_Out[candidate+230] without a bound check; lags beyond the
+ *   array count as below threshold here. */
+int ofdm_packet_detect(ofdm_ctx *ctx, const float *rx_dev, float *corr_dev, long n, int len);
+int ofdm_packet_select(ofdm_ctx *ctx, const float *corr_dev, int32_t *idx_dev, long n, int len_corr);
+
 /* Multi-GPU glue: split device counters [n] into homogeneous buffers (ints [n][5] uint64: bit_errors, bits,
  * frames_in_error, rail_errors, frames; dbls [n][3]: sum_err2, sum_ref2, sum_evm_lin) for a sum all-reduce
  * (ncclUint64 / ncclDouble), and merge them back.  The all-reduce is the path's only exchange. */

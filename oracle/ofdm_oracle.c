@@ -497,3 +497,51 @@ void orc_rrc_rx(const float *in, int in_len, int packet_idx, int frame_len, floa
     for (int i = packet_idx; i < 2 * frame_len + packet_idx - 1; i += 2) r[index++] = f[i];
     free(f);
 }
+
+/* ---------------- section 8(f) rank 2: packet detection / selection (OFDM.c:659-771) ----------------
+ * Packet_Detection: delay 16, window 32, no conjugate (as the reference and its MATLAB model): per lag i
+ *   corr  = sum_k r[i+k]*r[i+k+16]          float complex, sequential, product (ac-bd, ad+bc) in float
+ *   peak  = sum_k cabs(r[i+k+16])^2          double terms added into a float accumulator
+ *   out_i = (float)( cabs(corr)^2 / (double)(float)(peak*peak) )      (libgcc __divdc3 with zero imaginary parts = a/c)
+ * Packet_Selection: threshold 0.75, gaps > 300 open a packet, the correlation 230 lags later must still be above
+ * the threshold, result = front + len_RRC_rx + 1 (= +11), 0 when nothing qualifies.  The reference reads
+ * Corr_Out[front+230] without a bound check; here (and on the GPU) lags beyond the array count as below threshold. */
+void orc_packet_detection(const float *rx, int len, float *corr_out)
+{
+    const cf32 *r = (const cf32 *)rx;
+    int n = len - 47;
+    for (int i = 0; i < n; ++i) {
+        float cr = 0.0f, ci = 0.0f, peak = 0.0f;
+        for (int k = 0; k < 32; ++k) {
+            cf32 a = r[i + k], b = r[i + k + 16];
+            float pr = a.re * b.re - a.im * b.im, pi = a.re * b.im + a.im * b.re;
+            cr += pr; ci += pi;
+            double h = hypot((double)b.re, (double)b.im);
+            peak = (float)((double)peak + h * h);
+        }
+        double hc = hypot((double)cr, (double)ci);
+        float p2 = peak * peak;
+        corr_out[2 * i] = (float)((hc * hc) / (double)p2);
+        corr_out[2 * i + 1] = (float)(0.0 / (double)p2);      /* 0/0 = NaN for an all-zero window, as __divdc3 gives */
+    }
+}
+int orc_packet_selection(const float *corr, int len_corr)
+{
+    int *idx = (int *)malloc(sizeof(int) * (size_t)(len_corr + 1)), count = 0;
+    for (int i = 0; i < len_corr; ++i) if (fabs((double)corr[2 * i]) > 0.75f && corr[2 * i + 1] == 0.0f) idx[count++] = i;
+    int result = 0, fronts = 0, prev_front = -1;
+    /* fronts: positions j in 0..count with idx[j] - idx[j-1] > 300 (idx[-1] = -1); the loop at :754 skips the last one */
+    int n_fronts = 0;
+    for (int j = 0; j < count; ++j) { int b = j ? idx[j - 1] : -1; if (idx[j] - b > 300) ++n_fronts; }
+    for (int j = 0; j < count && result == 0; ++j) {
+        int b = j ? idx[j - 1] : -1;
+        if (idx[j] - b <= 300) continue;
+        ++fronts;
+        if (fronts > n_fronts - 1) break;                      /* x < packet_front_count - 1 */
+        int look = idx[j] + 230;
+        if (look < len_corr && fabs((double)corr[2 * look]) > 0.75f) result = idx[j] + 10 + 1;
+    }
+    (void)prev_front;
+    free(idx);
+    return result;
+}

@@ -55,4 +55,6 @@ void  orc_chain_multipath(const uint8_t *bits, const float *g, const float *taps
 void  orc_rrc_taps(float *out21);
 void  orc_rrc_tx(const float *frame, int len, float *out /* (2*len+20)*2 */);
 void  orc_rrc_rx(const float *in, int in_len, int packet_idx, int frame_len, float *out /* frame_len*2 */);
+void  orc_packet_detection(const float *rx, int len, float *corr_out /* (len-47)*2 */);
+int   orc_packet_selection(const float *corr, int len_corr);
 #endif

@@ -165,6 +165,17 @@ class _Base:
             self._f("rrc_rx")(_p(xr[i]), C.c_int(xr.shape[1]), C.c_int(packet_idx), C.c_int(frame_len), _p(out[i]))
         return out
 
+    def packet_detection(self, rx):
+        rx = _f32(rx).reshape(-1, 2)
+        out = np.zeros((rx.shape[0] - 47, 2), np.float32)
+        self._f("packet_detection")(_p(rx), C.c_int(rx.shape[0]), _p(out))
+        return out
+
+    def packet_selection(self, corr):
+        corr = _f32(corr).reshape(-1, 2)
+        self._f("packet_selection").restype = C.c_int
+        return int(self._f("packet_selection")(_p(corr), C.c_int(corr.shape[0])))
+
     def chain(self, bits, g, n_sym, snr_db, noise_mode=0, per_frame=False):
         bits = _u8(bits).reshape(-1, 96 * n_sym)
         n = bits.shape[0]
@@ -211,6 +222,13 @@ class Ref(_Base):
             return self.lib.ref_main_default(C.c_uint(seed), C.c_int(quiet))
         finally:
             os.chdir(cwd)
+
+    def transmit_full(self):
+        """Transmitter(): the reference's own 9800-sample over-the-air waveform (STS, LTS, 2 symbols, x2, RRC, x10)."""
+        out = np.zeros((12000, 2), np.float32)
+        self.lib.ref_transmit_full.restype = C.c_int
+        n = self.lib.ref_transmit_full(_p(out), C.c_int(12000))
+        return out[:n]
 
     def write_complex(self, a, fname):
         a = _f32(a).reshape(-1, 2)

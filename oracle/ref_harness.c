@@ -427,3 +427,36 @@ void ref_rrc_taps(float *out21)
 {
     for (int i = 0; i < 21; ++i) out21[i] = crealf(RRC_Filter_Tx[i]);
 }
+
+/* ---- section 8(f) rank 2: packet detection / selection, the reference's own functions (:659-771) ---- */
+int ref_transmit_full(float *out, int max_len)      /* Transmitter() :467 -> the 10x repeated, RRC-shaped waveform (9800 samples) */
+{
+    hush();
+    float complex *tx = Transmitter();
+    unhush();
+    int n = len_Tx_Signal_repeated;
+    if (n > max_len) n = max_len;
+    put(out, tx, n);
+    free(tx); free(Data); Data = NULL;
+    Deallocate_Array_2D(Data_Payload_Mod, data_frames_number); Data_Payload_Mod = NULL;
+    return len_Tx_Signal_repeated;
+}
+int ref_packet_detection(const float *rx, int len, float *corr_out /* (len-47)*2 */)
+{
+    float complex *x = Allocate_Array_1D(len);
+    get(x, rx, len);
+    int n = 0;
+    float complex *c = Packet_Detection(x, len, &n);
+    put(corr_out, c, n);
+    free(x); free(c);
+    return n;
+}
+int ref_packet_selection(const float *corr, int len_corr)
+{
+    /* Packet_Selection reads Corr_Out[front + 230] (:756) without a bound check: give it zero padding to read */
+    float complex *c = Allocate_Array_1D(len_corr + 256);
+    get(c, corr, len_corr);
+    int idx = Packet_Selection(c, len_corr);
+    free(c);
+    return idx;
+}

@@ -64,6 +64,8 @@ def main():
             out[tag + "ota_%d" % i] = ota
             for k in ("H", "eq", "sliced", "bits", "evm_lin", "evm_db", "evm_agc_lin", "evm_agc_db", "ber", "bit_errors", "rail_errors"):
                 out[tag + "rx_%s_%d" % (k, i)] = r[k]
+    # the reference's own over-the-air waveform (Transmitter(): STS, LTS, 2 symbols of "Hey! I am Vivaswan", x2, RRC, x10)
+    out["ref_tx_waveform"] = ref.transmit_full()
     # whole-chain totals
     n_sym, n_frames = 2, 256
     bits = rng.integers(0, 2, (n_frames, 96 * n_sym), dtype=np.uint8)

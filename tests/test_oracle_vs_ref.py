@@ -125,3 +125,23 @@ def test_rrc_pulse_shaping_port_matches_reference(port, ref):
         assert same(port.rrc_rx(noisy, idx, 320), ref.rrc_rx(noisy, idx, 320))
     # aligned at the filter-pair delay the chain is recovered up to the RRC pair's residual ISI
     assert np.max(np.abs(ref.rrc_rx(shaped, 20, 320) - tx)) < 0.04
+
+
+def test_packet_detection_selection_port_matches_reference(port, ref, golden):
+    """SURVEY 8(f) rank 2 on captures of the reference's own waveform, with its own channel and libc noise."""
+    tx = ref.transmit_full()
+    assert same(tx, golden["ref_tx_waveform"])
+    rng = np.random.default_rng(4)
+    found = 0
+    for trial in range(24):
+        ota = ref.awgn(tx, float([3, 8, 15, 30][trial % 4]), seed=500 + trial)
+        start = int(rng.integers(0, 9800 - 3008))
+        cap = ota[start:start + 3008]
+        cr = ref.packet_detection(cap)
+        assert same(port.packet_detection(cap), cr)
+        idx = ref.packet_selection(cr)
+        assert port.packet_selection(cr) == idx
+        found += idx > 0
+    assert found >= 10
+    z = np.zeros((3008, 2), np.float32)
+    assert same(port.packet_detection(z), ref.packet_detection(z)) and port.packet_selection(ref.packet_detection(z)) == 0
