@@ -99,6 +99,12 @@ SIGNATURES = {
     "ofdm_awgn_inject_len": (_I, [_VP, _VP, _VP, _VP, _F, _VP, _L, _I, _I]),
     "ofdm_packet_detect": (_I, [_VP, _VP, _VP, _L, _I]),
     "ofdm_packet_select": (_I, [_VP, _VP, _VP, _L, _I]),
+    "ofdm_sts": (_I, [_VP, _VP]),
+    "ofdm_prepend_sts": (_I, [_VP, _VP, _VP, _L, _I]),
+    "ofdm_gather": (_I, [_VP, _VP, _VP, _I, _VP, _L, _I, _I]),
+    "ofdm_rrc_rx_idx": (_I, [_VP, _VP, _VP, _VP, _L, _I, _I]),
+    "ofdm_cfo_coarse": (_I, [_VP, _VP, _VP, _VP, _L, _I]),
+    "ofdm_cfo_fine": (_I, [_VP, _VP, _VP, _VP, _L, _I]),
     "ofdm_counters_pack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_unpack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_finalize": (_I, [C.POINTER(Counters), C.POINTER(_F)]),
@@ -390,6 +396,41 @@ class Ofdm:
         idx = self.empty((corr.shape[0],), self.torch.int32)
         self._check(self.lib.ofdm_packet_select(self.h, _ptr(corr), _ptr(idx), corr.shape[0], corr.shape[1]))
         return idx
+
+    def sts(self):
+        t = np.zeros((160, 2), np.float32)
+        self._check(self.lib.ofdm_sts(self.h, t.ctypes.data))
+        return t
+
+    def prepend_sts(self, frames):
+        n, length = frames.shape[0], frames.shape[1]
+        out = self.empty((n, 160 + length, 2), self.torch.float32)
+        self._check(self.lib.ofdm_prepend_sts(self.h, _ptr(frames), _ptr(out), n, length))
+        return out
+
+    def gather(self, x, start, out_len):
+        """start: int (same for all) or an int32 device tensor [n]"""
+        n, in_len = x.shape[0], x.shape[1]
+        out = self.empty((n, out_len, 2), self.torch.float32)
+        if isinstance(start, int):
+            self._check(self.lib.ofdm_gather(self.h, _ptr(x), None, start, _ptr(out), n, in_len, out_len))
+        else:
+            self._check(self.lib.ofdm_gather(self.h, _ptr(x), _ptr(start), 0, _ptr(out), n, in_len, out_len))
+        return out
+
+    def rrc_rx_idx(self, x, idx, frame_len_):
+        n, in_len = x.shape[0], x.shape[1]
+        out = self.empty((n, frame_len_, 2), self.torch.float32)
+        self._check(self.lib.ofdm_rrc_rx_idx(self.h, _ptr(x), _ptr(idx), _ptr(out), n, in_len, frame_len_))
+        return out
+
+    def cfo(self, x, fine):
+        n, length = x.shape[0], x.shape[1]
+        out = self.empty((n, length, 2), self.torch.float32)
+        freq = self.empty((n,), self.torch.float32)
+        fn = self.lib.ofdm_cfo_fine if fine else self.lib.ofdm_cfo_coarse
+        self._check(fn(self.h, _ptr(x), _ptr(out), _ptr(freq), n, length))
+        return out, freq
 
     def finalize(self, counters):
         res = (_F * 3)()

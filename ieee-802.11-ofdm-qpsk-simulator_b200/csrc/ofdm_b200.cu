@@ -22,6 +22,8 @@ struct ofdm_ctx {
     char err[256] = {0};
     float lts_freq[128];
     float lts_time[320];
+    float sts_time[320];
+    float *sts_dev = nullptr;
     float lts_power_prefix = 0.0f;
     // cached scratch (grown on demand, released with the context)
     void *scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -280,6 +282,23 @@ int ofdm_ctx_create(ofdm_ctx **out, int device)
             st = upload_tables(ctx, ctx->lts_time);
         }
     }
+    // STS: Preamble_Generator(type 0) OFDM.c:479-492: S_k * (float)sqrt(13/6) at c = 6..58, exact ifft, first 16 samples x 10 (:393)
+    if (st == OFDM_OK) {
+        static const signed char Sk[53] = {0,0,1,0,0,0,-1,0,0,0, 1,0,0,0,-1,0,0,0,-1,0,0,0, 1,0,0,0,0,0,0,0,-1,0,0,0, -1,0,0,0,1,0,0,0,1,0,0,0, 1,0,0,0,1,0,0};
+        const float scale = (float)sqrt(13.0 / 6.0);
+        float grid[128], t64[128];
+        memset(grid, 0, sizeof grid);
+        for (int i = 0; i < 53; ++i) { grid[2 * (6 + i)] = (float)Sk[i] * scale; grid[2 * (6 + i) + 1] = (float)Sk[i] * scale; }
+        if (cudaMemcpyAsync(d_buf, grid, sizeof grid, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+        if (st == OFDM_OK) st = launch_fft<true, true>(ctx, d_buf, d_buf + 128, 1);
+        if (st == OFDM_OK && cudaMemcpyAsync(t64, d_buf + 128, sizeof t64, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+        if (st == OFDM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+        if (st == OFDM_OK) {
+            for (int r = 0; r < 10; ++r) memcpy(ctx->sts_time + 32 * r, t64, 16 * 2 * sizeof(float));
+            if (cudaMalloc(&ctx->sts_dev, sizeof ctx->sts_time) != cudaSuccess) st = OFDM_ERR_NOMEM;
+            else if (cudaMemcpy(ctx->sts_dev, ctx->sts_time, sizeof ctx->sts_time, cudaMemcpyHostToDevice) != cudaSuccess) st = OFDM_ERR_CUDA;
+        }
+    }
     if (d_buf) cudaFree(d_buf);
     if (st != OFDM_OK) { ofdm_ctx_destroy(ctx); return st; }
     *out = ctx;
@@ -292,6 +311,7 @@ int ofdm_ctx_destroy(ofdm_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 6; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->sts_dev) cudaFree(ctx->sts_dev);
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
@@ -855,6 +875,68 @@ int ofdm_packet_select(ofdm_ctx *ctx, const float *corr, int32_t *idx, long n, i
     k_packet_select<<<blocks_1d(n), 256, 0, ctx->stream>>>(corr, idx, n, len_corr);
     return check_launch(ctx, "k_packet_select");
 }
+
+// ------------------------------------------------------------------ CFO and full-path glue
+int ofdm_sts(ofdm_ctx *ctx, float *sts_time_host)
+{
+    if (!ctx || !sts_time_host) return OFDM_ERR_INVALID;
+    memcpy(sts_time_host, ctx->sts_time, sizeof ctx->sts_time);
+    return OFDM_OK;
+}
+int ofdm_prepend_sts(ofdm_ctx *ctx, const float *frames, float *out, long n_frames, int frame_len)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1);
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, frames != nullptr && out != nullptr && frames != out);
+    long total = n_frames * (160 + (long)frame_len);
+    int grid = (int)((total + 255) / 256 < 4L * ctx->sm_count * 8 ? (total + 255) / 256 : 4L * ctx->sm_count * 8);
+    k_prepend<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(ctx->sts_dev), 160, reinterpret_cast<const float2 *>(frames),
+                                             reinterpret_cast<float2 *>(out), n_frames, frame_len);
+    return check_launch(ctx, "k_prepend");
+}
+int ofdm_gather(ofdm_ctx *ctx, const float *in, const int32_t *start, int start_scalar, float *out, long n, int in_len, int out_len)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0 && in_len >= 1 && out_len >= 1 && (start != nullptr || start_scalar >= 0));
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && in != out);
+    long total = n * (long)out_len;
+    int grid = (int)((total + 255) / 256 < 4L * ctx->sm_count * 8 ? (total + 255) / 256 : 4L * ctx->sm_count * 8);
+    k_gather<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(in), start, start_scalar, reinterpret_cast<float2 *>(out), n, in_len, out_len);
+    return check_launch(ctx, "k_gather");
+}
+int ofdm_rrc_rx_idx(ofdm_ctx *ctx, const float *in, const int32_t *idx, float *out, long n_frames, int in_len, int frame_len)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && in_len >= 1 && in_len <= 12000 && frame_len >= 1);
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && idx != nullptr && in != out);
+    const size_t smem = (size_t)kWarpsPerBlock * in_len * sizeof(float2);
+    OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx_idx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = grid_for(ctx, k_rrc_rx_idx, smem, kWarpsPerBlock, n_frames);
+    k_rrc_rx_idx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), idx, reinterpret_cast<float2 *>(out), n_frames, in_len, frame_len);
+    return check_launch(ctx, "k_rrc_rx_idx");
+}
+static int cfo_common(ofdm_ctx *ctx, bool fine, const float *rx, float *out, float *freq, long n, int len)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n >= 0 && len >= (fine ? 320 : 112));
+    if (n == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, rx != nullptr && out != nullptr && rx != out);
+    const float2 *x = reinterpret_cast<const float2 *>(rx);
+    float2 *y = reinterpret_cast<float2 *>(out);
+    if (fine) {
+        int grid = grid_for(ctx, k_cfo<true>, 0, kWarpsPerBlock, n);
+        k_cfo<true><<<grid, kThreads, 0, ctx->stream>>>(x, y, freq, n, len);
+    } else {
+        int grid = grid_for(ctx, k_cfo<false>, 0, kWarpsPerBlock, n);
+        k_cfo<false><<<grid, kThreads, 0, ctx->stream>>>(x, y, freq, n, len);
+    }
+    return check_launch(ctx, "k_cfo");
+}
+int ofdm_cfo_coarse(ofdm_ctx *ctx, const float *rx, float *out, float *freq, long n, int len) { return cfo_common(ctx, false, rx, out, freq, n, len); }
+int ofdm_cfo_fine(ofdm_ctx *ctx, const float *rx, float *out, float *freq, long n, int len) { return cfo_common(ctx, true, rx, out, freq, n, len); }
 
 int ofdm_counters_pack(ofdm_ctx *ctx, const ofdm_counters *counters, int n, uint64_t *ints, double *dbls)
 {

@@ -675,4 +675,110 @@ __global__ void k_packet_select(const float *__restrict__ corr, int32_t *__restr
     idx_out[c] = result;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CFO estimation / correction (OFDM.c:773-828) and the glue of the reference's full
+// over-the-air path (STS slot :483-492/:572, 10x repetition :607-612, capture window :945-955, per-packet
+// decimation :986-996).
+//
+// CFO: the correlation sum_i a[i]*conj(b[i]) uses the DOUBLE conj(), so every product is formed in double and the
+// float complex accumulator takes (float)((double)acc + product), sequentially (lane 0).  freq = (float)(K * atan2)
+// and the rotator cexp(-I*2*PI*f*ts*i) are double libm calls in the reference: the device's atan2 / sincos agree
+// with glibc to an ulp of double, which the following roundings to float absorb except with probability ~1e-8 per
+// sample -- this stage is specified to 1e-6 relative, not bit-exact.  Coarse: slots 5/6 of the STS (samples 80..111),
+// product with the rotator in double.  Fine: the LTS halves (192..319), rotator rounded to float first (exp_term),
+// product in float.
+template <bool FINE>
+__global__ void __launch_bounds__(kThreads) k_cfo(const float2 *__restrict__ rx, float2 *__restrict__ out, float *__restrict__ freq_out,
+                                                  long n, int len)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kA = FINE ? 192 : 80, kB = FINE ? 256 : 96, kN = FINE ? 64 : 16;
+    constexpr double kPi = 3.14159265358979323846, kTs = 1 / 20e6;                       // PI :13, ts_sec :17
+    const double kScale = -1.0 / (2 * kPi * kN * kTs);                                   // :798 / :821
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float2 *x = rx + f * len;
+        float fr = 0.f;
+        if (lane == 0) {
+            float accr = 0.f, acci = 0.f;
+            for (int i = 0; i < kN; ++i) {
+                const float2 a = x[kA + i], b = x[kB + i];
+                const double ar = a.x, ai = a.y, br = b.x, nbi = -(double)b.y;
+                const double pr = __dsub_rn(__dmul_rn(ar, br), __dmul_rn(ai, nbi)), pi = __dadd_rn(__dmul_rn(ar, nbi), __dmul_rn(ai, br));
+                accr = __double2float_rn(__dadd_rn((double)accr, pr));
+                acci = __double2float_rn(__dadd_rn((double)acci, pi));
+            }
+            fr = __double2float_rn(__dmul_rn(kScale, atan2((double)acci, (double)accr)));
+            if (freq_out != nullptr) freq_out[f] = fr;
+        }
+        fr = __shfl_sync(0xffffffffu, fr, 0);
+        const double w = __dmul_rn(__dmul_rn(__dmul_rn(-2.0, kPi), (double)fr), kTs);   // ((-2*PI)*f)*ts, the reference's association
+        for (int i = lane; i < len; i += 32) {
+            double s, c;
+            sincos(__dmul_rn(w, (double)i), &s, &c);
+            const float2 v = x[i];
+            float2 y;
+            if (FINE) {
+                const float cf = __double2float_rn(c), sf = __double2float_rn(s);
+                y.x = __fsub_rn(__fmul_rn(v.x, cf), __fmul_rn(v.y, sf));
+                y.y = __fadd_rn(__fmul_rn(v.x, sf), __fmul_rn(v.y, cf));
+            } else {
+                y.x = __double2float_rn(__dsub_rn(__dmul_rn((double)v.x, c), __dmul_rn((double)v.y, s)));
+                y.y = __double2float_rn(__dadd_rn(__dmul_rn((double)v.x, s), __dmul_rn((double)v.y, c)));
+            }
+            out[f * len + i] = y;
+        }
+    }
+}
+
+// out[f][j] = in[f][(start_f + j) % in_len], j < out_len: Slice_Repeater (:193) generalised -- prefix slices (:955),
+// tiling (:612: start 0, out_len = r * in_len) and capture windows of the repeated waveform all come out of it.
+__global__ void k_gather(const float2 *__restrict__ in, const int32_t *__restrict__ start, int start_scalar, float2 *__restrict__ out,
+                         long n, int in_len, int out_len)
+{
+    const long total = n * out_len;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long f = t / out_len; const int j = (int)(t - f * out_len);
+        const int s = start != nullptr ? start[f] : start_scalar;
+        out[t] = in[f * in_len + (int)(((long)s + j) % in_len)];
+    }
+}
+// frame -> prefix || frame (the STS slot in front of LTS || data, :572-581)
+__global__ void k_prepend(const float2 *__restrict__ prefix, int prefix_len, const float2 *__restrict__ in, float2 *__restrict__ out, long n, int len)
+{
+    const int out_len = prefix_len + len;
+    const long total = n * out_len;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long f = t / out_len; const int j = (int)(t - f * out_len);
+        out[t] = j < prefix_len ? prefix[j] : in[f * len + (j - prefix_len)];
+    }
+}
+// matched filter + decimation with a per-capture packet index (:965, :986-996).  Filtered samples past the end of
+// the capture (which the reference would read out of bounds when a packet starts late in the window) count as zero.
+__global__ void __launch_bounds__(kThreads) k_rrc_rx_idx(const float2 *__restrict__ in, const int32_t *__restrict__ idx, float2 *__restrict__ out,
+                                                         long n_frames, int in_len, int frame_len)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * in_len;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        for (int i = lane; i < in_len; i += 32) sx[i] = in[f * in_len + i];
+        __syncwarp();
+        const int p0 = idx[f];
+        for (int r = lane; r < frame_len; r += 32) {
+            const int k = p0 + 2 * r;
+            float ar = 0.f, ai = 0.f;
+            if (k < in_len + 20) {
+                const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < in_len - 1 ? k : in_len - 1;
+                for (int i = lo; i <= hi; ++i) {
+                    const float2 a = sx[i];
+                    const float h = c_rrc[k - i];
+                    ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
+                }
+            }
+            out[f * frame_len + r] = make_float2(ar, ai);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace ofdm

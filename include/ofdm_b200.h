@@ -207,6 +207,27 @@ int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx_dev, const float *g_dev,
 int ofdm_packet_detect(ofdm_ctx *ctx, const float *rx_dev, float *corr_dev, long n, int len);
 int ofdm_packet_select(ofdm_ctx *ctx, const float *corr_dev, int32_t *idx_dev, long n, int len_corr);
 
+/* ---- CFO stages and full-path glue ----
+ * Frames here are the reference's 480-sample layout STS(160) || LTS(160) || data (OFDM.c:569-581) or longer.
+ * ofdm_sts: host copy of the short-preamble slot, Preamble_Generator(type 0), OFDM.c:479-492 (bit-exact).
+ * ofdm_prepend_sts: [n][frame_len] -> [n][160 + frame_len] (OFDM.c:572-581).
+ * ofdm_gather: out[f][j] = in[f][(start_f + j) % in_len], j < out_len; start_dev [n] or NULL + start_scalar.  This is
+ *   Slice_Repeater (OFDM.c:193): tiling (x10 repetition :607-612: start 0, out_len = 10*in_len), capture windows
+ *   (:945-955) and plain slices (dropping the STS: start 160).
+ * ofdm_rrc_rx_idx: ofdm_rrc_rx with a per-capture packet index (OFDM.c:978-996); filtered samples past the capture
+ *   (an out-of-bounds read in the reference when a packet starts late) count as zero.
+ * ofdm_cfo_coarse / ofdm_cfo_fine: Coarse_CFO_Estimation OFDM.c:773-804 (STS slots 5/6) and Fine_CFO_Estimation
+ *   OFDM.c:806-828 (LTS halves): estimate + derotation; freq_dev [n] (nullable) receives the float estimates.
+ *   The reference calls double libm atan2 / cexp here; agreement is specified to 1e-6 relative. */
+int ofdm_sts(ofdm_ctx *ctx, float *sts_time_host);
+int ofdm_prepend_sts(ofdm_ctx *ctx, const float *frames_dev, float *out_dev, long n_frames, int frame_len);
+int ofdm_gather(ofdm_ctx *ctx, const float *in_dev, const int32_t *start_dev, int start_scalar, float *out_dev, long n,
+                int in_len, int out_len);
+int ofdm_rrc_rx_idx(ofdm_ctx *ctx, const float *in_dev, const int32_t *idx_dev, float *out_dev, long n_frames, int in_len,
+                    int frame_len);
+int ofdm_cfo_coarse(ofdm_ctx *ctx, const float *rx_dev, float *out_dev, float *freq_dev, long n, int len);
+int ofdm_cfo_fine(ofdm_ctx *ctx, const float *rx_dev, float *out_dev, float *freq_dev, long n, int len);
+
 /* Multi-GPU glue: split device counters [n] into homogeneous buffers (ints [n][5] uint64: bit_errors, bits,
  * frames_in_error, rail_errors, frames; dbls [n][3]: sum_err2, sum_ref2, sum_evm_lin) for a sum all-reduce
  * (ncclUint64 / ncclDouble), and merge them back.  The all-reduce is the path's only exchange. */

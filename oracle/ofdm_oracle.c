@@ -545,3 +545,66 @@ int orc_packet_selection(const float *corr, int len_corr)
     free(idx);
     return result;
 }
+
+/* ---------------- section 8(f) ranks 3/4: short preamble and CFO stages (OFDM.c:483-492, 773-828) ---------------- */
+void orc_sts_time(float *out160)
+{
+    orc_init();
+    /* S_k :483-490 scaled by (float)sqrt(13/6) :479, placed at c = 6..58, ifft, first 16 samples x 10 (:393) */
+    static const signed char Sk[53] = {0,0,1,0,0,0,-1,0,0,0, 1,0,0,0,-1,0,0,0,-1,0,0,0, 1,0,0,0,0,0,0,0,-1,0,0,0, -1,0,0,0,1,0,0,0,1,0,0,0, 1,0,0,0,1,0,0};
+    float scale = (float)sqrt(13.0 / 6.0);
+    cf32 grid[64], t[64];
+    memset(grid, 0, sizeof grid);
+    for (int i = 0; i < 53; ++i) { grid[6 + i].re = (float)Sk[i] * scale; grid[6 + i].im = (float)Sk[i] * scale; }
+    ifft_centred(grid, t);
+    cf32 *o = (cf32 *)out160;
+    for (int r = 0; r < 10; ++r) for (int i = 0; i < 16; ++i) o[16 * r + i] = t[i];
+}
+
+static const double TS_SEC = 1 / 20e6;      /* ts_sec :17 */
+
+/* sum_i a[i]*conj(b[i]) (:793-796, :816-819).  conj() is the DOUBLE complex function, so each product is formed in
+ * double (float*float products are exact there; one rounding for the sum) and the float complex accumulator takes
+ * (float)((double)acc + product), sequentially. */
+static cf32 conj_dot(const cf32 *a, const cf32 *b, int n)
+{
+    cf32 acc = {0.0f, 0.0f};
+    for (int i = 0; i < n; ++i) {
+        double ar = a[i].re, ai = a[i].im, br = b[i].re, nbi = -(double)b[i].im;
+        double pr = ar * br - ai * nbi, pi = ar * nbi + ai * br;
+        acc.re = (float)((double)acc.re + pr); acc.im = (float)((double)acc.im + pi);
+    }
+    return acc;
+}
+/* coarse (:802): rx[i] * cexp(...) evaluated in double, rounded to float once.
+ * fine (:825-826): the rotator is first stored in a FLOAT complex (exp_term), then multiplied in float. */
+static void derotate(const cf32 *x, cf32 *y, int len, float freq, int rotator_in_float)
+{
+    for (int i = 0; i < len; ++i) {
+        double ang = -2.0 * PI_REF * (double)freq * TS_SEC * i;     /* imaginary part of -I*2*PI*f*ts*i, same association */
+        double c = cos(ang), s = sin(ang);
+        if (rotator_in_float) {
+            float cf = (float)c, sf = (float)s;
+            y[i].re = x[i].re * cf - x[i].im * sf;
+            y[i].im = x[i].re * sf + x[i].im * cf;
+        } else {
+            double xr = x[i].re, xi = x[i].im;
+            y[i].re = (float)(xr * c - xi * s);
+            y[i].im = (float)(xr * s + xi * c);
+        }
+    }
+}
+void orc_cfo_coarse(const float *rx, int len, float *out)
+{
+    const cf32 *x = (const cf32 *)rx;
+    cf32 p = conj_dot(x + 80, x + 96, 16);                                                     /* STS slots 5 and 6 */
+    float f = (float)((-1.0 / (2 * PI_REF * 16 * TS_SEC)) * atan2((double)p.im, (double)p.re));   /* :798 */
+    derotate(x, (cf32 *)out, len, f, 0);
+}
+void orc_cfo_fine(const float *rx, int len, float *out)
+{
+    const cf32 *x = (const cf32 *)rx;
+    cf32 p = conj_dot(x + 192, x + 256, 64);                                                   /* the two LTS halves */
+    float f = (float)((-1.0 / (2 * PI_REF * 64 * TS_SEC)) * atan2((double)p.im, (double)p.re));   /* :821 */
+    derotate(x, (cf32 *)out, len, f, 1);
+}

@@ -57,4 +57,7 @@ void  orc_rrc_tx(const float *frame, int len, float *out /* (2*len+20)*2 */);
 void  orc_rrc_rx(const float *in, int in_len, int packet_idx, int frame_len, float *out /* frame_len*2 */);
 void  orc_packet_detection(const float *rx, int len, float *corr_out /* (len-47)*2 */);
 int   orc_packet_selection(const float *corr, int len_corr);
+void  orc_sts_time(float *out160);
+void  orc_cfo_coarse(const float *rx, int len, float *out);
+void  orc_cfo_fine(const float *rx, int len, float *out);
 #endif

@@ -165,6 +165,23 @@ class _Base:
             self._f("rrc_rx")(_p(xr[i]), C.c_int(xr.shape[1]), C.c_int(packet_idx), C.c_int(frame_len), _p(out[i]))
         return out
 
+    def sts_time(self):
+        out = np.zeros((160, 2), np.float32)
+        self._f("sts_time")(_p(out))
+        return out
+
+    def cfo_coarse(self, rx):
+        rx = _f32(rx).reshape(-1, 2)
+        out = np.zeros_like(rx)
+        self._f("cfo_coarse")(_p(rx), C.c_int(rx.shape[0]), _p(out))
+        return out
+
+    def cfo_fine(self, rx):
+        rx = _f32(rx).reshape(-1, 2)
+        out = np.zeros_like(rx)
+        self._f("cfo_fine")(_p(rx), C.c_int(rx.shape[0]), _p(out))
+        return out
+
     def packet_detection(self, rx):
         rx = _f32(rx).reshape(-1, 2)
         out = np.zeros((rx.shape[0] - 47, 2), np.float32)
@@ -229,6 +246,14 @@ class Ref(_Base):
         self.lib.ref_transmit_full.restype = C.c_int
         n = self.lib.ref_transmit_full(_p(out), C.c_int(12000))
         return out[:n]
+
+    def full_point(self, seed_noise, seed_rx, snr_db):
+        """One SNR point of the reference's main(): returns (ota [9800,2], Res[3] = EVM_dB, EVM_AGC_dB, BER, rx_start)."""
+        ota = np.zeros((9800, 2), np.float32)
+        res = np.zeros(3, np.float32)
+        start = C.c_int(0)
+        self.lib.ref_full_point(C.c_uint(seed_noise), C.c_uint(seed_rx), C.c_float(snr_db), _p(ota), _p(res), C.byref(start))
+        return ota, res, start.value
 
     def write_complex(self, a, fname):
         a = _f32(a).reshape(-1, 2)

@@ -460,3 +460,61 @@ int ref_packet_selection(const float *corr, int len_corr)
     free(c);
     return idx;
 }
+
+/* ---- section 8(f) ranks 3/4: STS, CFO stages, the reference's own functions ---- */
+void ref_sts_time(float *out160)      /* Preamble_Generator(type 0) with S_k and scale as Transmitter() :479-492 passes them */
+{
+    float scale = sqrt(13.0 / 6.0);
+    float complex virtual_subcarrier[11] = {0};
+    float complex S_k[54] = {
+        0, 0, 1 + 1*I, 0, 0, 0, -1 - 1*I, 0, 0, 0,
+        1 + 1*I, 0, 0, 0, -1 - 1*I, 0, 0, 0, -1 - 1*I, 0, 0, 0,
+        1 + 1*I, 0, 0, 0, 0, 0, 0, 0, -1 - 1*I, 0, 0, 0,
+        -1 - 1*I, 0, 0, 0, 1 + 1*I, 0, 0, 0, 1 + 1*I, 0, 0, 0,
+        1 + 1*I, 0, 0, 0, 1 + 1*I, 0, 0, 0};
+    float complex sts[160];
+    float complex keep[64];
+    memcpy(keep, Long_preamble_slot_Frequency, sizeof keep);
+    Preamble_Generator(scale, S_k, virtual_subcarrier, sts, 0);
+    memcpy(Long_preamble_slot_Frequency, keep, sizeof keep);
+    put(out160, sts, 160);
+}
+void ref_cfo_coarse(const float *rx, int len, float *out)
+{
+    float complex *x = Allocate_Array_1D(len), *y = Allocate_Array_1D(len);
+    get(x, rx, len);
+    Coarse_CFO_Estimation(x, y, len);          /* :773 */
+    put(out, y, len);
+    free(x); free(y);
+}
+void ref_cfo_fine(const float *rx, int len, float *out)
+{
+    float complex *x = Allocate_Array_1D(len), *y = Allocate_Array_1D(len);
+    get(x, rx, len);
+    Fine_CFO_Estimation(x, y, len);            /* :806 */
+    put(out, y, len);
+    free(x); free(y);
+}
+
+/* ---- whole program: Transmitter() -> Transmission_Over_Air() -> Receiver(), the reference's own main() body for one
+ * SNR point (:1191, :1208, :1211), with the libc stream seeded so that the run can be replayed elsewhere: the noisy
+ * waveform is returned (to be injected), and so is the capture offset Receiver() will draw (rand() % ..., :949). */
+int ref_full_point(unsigned seed_noise, unsigned seed_rx, float snr_db, float *ota_out /* 9800*2 */, float *res /* 3 */, int *rx_start_out)
+{
+    hush();
+    float complex *tx = Transmitter();
+    int len = len_Tx_Signal_repeated;
+    float complex *ota = Allocate_Array_1D(len);
+    srand(seed_noise);
+    Transmission_Over_Air(tx, ota, snr_db, len);
+    put(ota_out, ota, len);
+    srand(seed_rx);
+    int len_rx = len * 0.307;
+    *rx_start_out = rand() % (len - len_rx);
+    srand(seed_rx);
+    Receiver(ota, len, data_frames_number, res);
+    unhush();
+    free(tx); free(ota); free(Data); Data = NULL;
+    Deallocate_Array_2D(Data_Payload_Mod, data_frames_number); Data_Payload_Mod = NULL;
+    return len;
+}

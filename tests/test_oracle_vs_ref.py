@@ -145,3 +145,31 @@ def test_packet_detection_selection_port_matches_reference(port, ref, golden):
     assert found >= 10
     z = np.zeros((3008, 2), np.float32)
     assert same(port.packet_detection(z), ref.packet_detection(z)) and port.packet_selection(ref.packet_detection(z)) == 0
+
+
+def test_sts_cfo_and_whole_receiver_port_matches_reference(port, ref):
+    """the port's STS and CFO stages equal the reference's functions bit for bit (same libm),
+    and the port's stages composed like Receiver() (OFDM.c:941-1165) reproduce Res[] of the reference's own
+    Transmitter -> Transmission_Over_Air -> Receiver run, including the runs where detection fails (packet_idx = 0)."""
+    assert same(port.sts_time(), ref.sts_time())
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2, (20, 192), dtype=np.uint8)
+    fr = np.concatenate([np.broadcast_to(ref.sts_time(), (20, 160, 2)), ref.tx_frames(bits, 2)], axis=1)
+    fr = fr + rng.standard_normal(fr.shape).astype(np.float32) * np.float32(0.05)
+    for f in fr:
+        a = ref.cfo_coarse(f)
+        assert same(port.cfo_coarse(f), a) and same(port.cfo_fine(a), ref.cfo_fine(a))
+    msg = b"Hey! I am Vivaswan" + b" " * 6
+    mbits = np.unpackbits(np.frombuffer(msg, np.uint8)).reshape(1, 192)
+    checked = 0
+    for k, snr in enumerate([6.0, 7.0, 8.0, 9.0, 10.0, 12.0, 15.0, 20.0, 30.0, 40.0]):
+        ota, res, start = ref.full_point(10 + k, 20 + k, snr)
+        cap = ota[start:start + 3008]
+        idx = port.packet_selection(port.packet_detection(cap))
+        if idx + 2 * 479 >= 3008 + 20:
+            continue                                  # the reference reads past Rx_filter_signal here (undefined)
+        rx = port.cfo_fine(port.cfo_coarse(port.rrc_rx(cap, idx, 480)[0]))
+        r = port.rx_frames(rx[160:], mbits, 2)
+        assert (r["evm_db"][0], r["evm_agc_db"][0], r["ber"][0]) == (res[0], res[1], res[2]), (snr, res)
+        checked += 1
+    assert checked >= 6
