@@ -105,6 +105,7 @@ SIGNATURES = {
     "ofdm_rrc_rx_idx": (_I, [_VP, _VP, _VP, _VP, _L, _I, _I]),
     "ofdm_cfo_coarse": (_I, [_VP, _VP, _VP, _VP, _L, _I]),
     "ofdm_cfo_fine": (_I, [_VP, _VP, _VP, _VP, _L, _I]),
+    "ofdm_awgn_philox_len": (_I, [_VP, _VP, _VP, _F, _U32, _U32, _U64, _VP, _L, _I, _I]),
     "ofdm_counters_pack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_unpack": (_I, [_VP, _VP, _I, _VP, _VP]),
     "ofdm_counters_finalize": (_I, [C.POINTER(Counters), C.POINTER(_F)]),
@@ -431,6 +432,12 @@ class Ofdm:
         fn = self.lib.ofdm_cfo_fine if fine else self.lib.ofdm_cfo_coarse
         self._check(fn(self.h, _ptr(x), _ptr(out), _ptr(freq), n, length))
         return out, freq
+
+    def awgn_philox_len(self, tx, snr_db, seed, stream, frame0, mode, power=None):
+        ota = self.empty(tuple(tx.shape), self.torch.float32)
+        self._check(self.lib.ofdm_awgn_philox_len(self.h, _ptr(tx), _ptr(power), snr_db, seed, stream, frame0, _ptr(ota), tx.shape[0],
+                                                  tx.shape[1], mode))
+        return ota
 
     def finalize(self, counters):
         res = (_F * 3)()

@@ -938,6 +938,28 @@ static int cfo_common(ofdm_ctx *ctx, bool fine, const float *rx, float *out, flo
 int ofdm_cfo_coarse(ofdm_ctx *ctx, const float *rx, float *out, float *freq, long n, int len) { return cfo_common(ctx, false, rx, out, freq, n, len); }
 int ofdm_cfo_fine(ofdm_ctx *ctx, const float *rx, float *out, float *freq, long n, int len) { return cfo_common(ctx, true, rx, out, freq, n, len); }
 
+int ofdm_awgn_philox_len(ofdm_ctx *ctx, const float *tx, const float *power, float snr_db, uint32_t seed, uint32_t stream, uint64_t frame0,
+                         float *ota, long n_frames, int frame_len, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= 2 * OFDM_FRAME_LEN(OFDM_MAX_SYM) + 64 && mode_ok(mode));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, tx != nullptr && ota != nullptr);
+    const float *pw = nullptr;
+    if (int st = resolve_power(ctx, tx, power, n_frames, frame_len, mode, &pw)) return st;
+    const float2 *x = reinterpret_cast<const float2 *>(tx);
+    float2 *y = reinterpret_cast<float2 *>(ota);
+    const float sl = snr_linear(snr_db);
+    if (mode == OFDM_MODE_EXACT) {
+        int grid = grid_for(ctx, k_awgn_philox_flat<true>, 0, kWarpsPerBlock, n_frames);
+        k_awgn_philox_flat<true><<<grid, kThreads, 0, ctx->stream>>>(x, pw, sl, seed, stream, frame0, y, n_frames, frame_len);
+    } else {
+        int grid = grid_for(ctx, k_awgn_philox_flat<false>, 0, kWarpsPerBlock, n_frames);
+        k_awgn_philox_flat<false><<<grid, kThreads, 0, ctx->stream>>>(x, pw, sl, seed, stream, frame0, y, n_frames, frame_len);
+    }
+    return check_launch(ctx, "k_awgn_philox_flat");
+}
+
 int ofdm_counters_pack(ofdm_ctx *ctx, const ofdm_counters *counters, int n, uint64_t *ints, double *dbls)
 {
     if (int st = bind(ctx)) return st;

@@ -232,6 +232,34 @@ __device__ __forceinline__ float add_noise(float xr, float g, double sigma_d, fl
     else return fmaf(sigma_f, g, xr);
 }
 
+// Philox noise for buffers that are not LTS||data frames (e.g. the oversampled, repeated waveform): consecutive
+// quadruples of samples share a block, domain 3.  One thread per block of four samples.
+template <bool EXACT>
+__global__ void __launch_bounds__(kThreads) k_awgn_philox_flat(const float2 *__restrict__ tx, const float *__restrict__ power, float snr_lin,
+                                                               uint32_t seed, uint32_t stream, uint64_t frame0, float2 *__restrict__ ota,
+                                                               long n_frames, int len)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float np = __fdiv_rn(power[f], snr_lin);
+        const double sigma_d = __dsqrt_rn((double)np);
+        const float sigma_f = (float)sigma_d;
+        for (int b = lane; 4 * b < len; b += 32) {
+            float z[4];
+            philox_normals4(seed, stream, frame0 + (uint64_t)f, (uint32_t)b, 3u, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = 4 * b + j;
+                if (n < len) {
+                    float2 s = tx[f * len + n];
+                    s.x = add_noise<EXACT>(s.x, z[j], sigma_d, sigma_f);
+                    ota[f * len + n] = s;
+                }
+            }
+        }
+    }
+}
+
 template <bool EXACT, int NOISE>
 __global__ void __launch_bounds__(kThreads) k_awgn(const float2 *__restrict__ tx, const float *__restrict__ g,
                                                    const float *__restrict__ power, float snr_lin, uint32_t seed,

@@ -10,7 +10,10 @@
  * Two payload sources:
  *   --message TEXT (default "Hey! I am Vivaswan", OFDM.c:20): Data_Generator's codec (OFDM.c:435-465,
  *       MSB-first ASCII bits, space-padded to a multiple of 96 bits), one frame, prints the received
- *       message per SNR point like Receiver() does (OFDM.c:1169-1182);
+ *       message per SNR point like Receiver() does (OFDM.c:1169-1182).  By default this mode runs the
+ *       reference's WHOLE over-the-air path (STS, x2 + RRC, x10 repetition, noise on the repeated waveform,
+ *       random capture window, packet detection / selection, matched filter + decimation, coarse + fine CFO,
+ *       then the stage chain), OFDM.c:467-618 and :941-1165; --stage-chain keeps only the stage chain;
  *   --frames N (N > 1): N frames of Philox random bits per SNR point through the fused Monte-Carlo kernel.
  *   --gpus N: the frames of the Monte-Carlo sweep are sharded across N GPUs of this node by global frame index
  *       (one context per GPU, all driven from this thread) and the counters are summed with ONE NCCL all-reduce
@@ -130,12 +133,14 @@ int main(int argc, char **argv)
     const char *message = "Hey! I am Vivaswan";          /* OFDM.c:20 */
     const char *outdir = "data", *dump = NULL;
     long frames = 1;
-    int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0, n_gpus = 1;
+    int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0, n_gpus = 1, full_chain = 1;
     float snr_start = 6.0f, snr_step = 1.0f;             /* OFDM.c:18, :1195-1198 */
     unsigned seed = 1;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
         if (!strcmp(a, "--quiet")) { quiet = 1; continue; }
+        if (!strcmp(a, "--stage-chain")) { full_chain = 0; continue; }
+        if (!strcmp(a, "--full-chain")) { full_chain = 1; continue; }
         if (!v) { fprintf(stderr, "missing value for %s\n", a); return 2; }
         if (!strcmp(a, "--message")) message = v;
         else if (!strcmp(a, "--frames")) frames = atol(v);
@@ -201,11 +206,40 @@ int main(int argc, char **argv)
             snprintf(path, sizeof path, "%s_complex.txt", dump);  CHECK(ofdm_write_complex_array_to_file(iq, len, path, 1));
             free(iq);
         }
+        /* whole over-the-air path: Transmitter() :569-617 once */
+        const int len480 = 160 + len, len_shaped = 2 * len480 + 20, len_rep = 10 * len_shaped;
+        const int len_cap = (int)(len_rep * 0.307);                                   /* :945 */
+        void *d_f480 = NULL, *d_shaped = NULL, *d_rep = NULL, *d_ota = NULL, *d_cap = NULL, *d_corr = NULL, *d_idx = NULL,
+             *d_rxf = NULL, *d_c1 = NULL, *d_c2 = NULL, *d_ld = NULL;
+        if (full_chain) {
+            CHECK(ofdm_dev_alloc(ctx, &d_f480, (size_t)len480 * 8));   CHECK(ofdm_dev_alloc(ctx, &d_shaped, (size_t)len_shaped * 8));
+            CHECK(ofdm_dev_alloc(ctx, &d_rep, (size_t)len_rep * 8));   CHECK(ofdm_dev_alloc(ctx, &d_ota, (size_t)len_rep * 8));
+            CHECK(ofdm_dev_alloc(ctx, &d_cap, (size_t)len_cap * 8));   CHECK(ofdm_dev_alloc(ctx, &d_corr, (size_t)len_cap * 4));
+            CHECK(ofdm_dev_alloc(ctx, &d_idx, 4));                     CHECK(ofdm_dev_alloc(ctx, &d_rxf, (size_t)len480 * 8));
+            CHECK(ofdm_dev_alloc(ctx, &d_c1, (size_t)len480 * 8));     CHECK(ofdm_dev_alloc(ctx, &d_c2, (size_t)len480 * 8));
+            CHECK(ofdm_dev_alloc(ctx, &d_ld, (size_t)len * 8));
+            CHECK(ofdm_prepend_sts(ctx, (const float *)d_frame, (float *)d_f480, 1, len));                    /* :572-581 */
+            CHECK(ofdm_rrc_tx(ctx, (const float *)d_f480, (float *)d_shaped, 1, len480));                     /* :587-605 */
+            CHECK(ofdm_gather(ctx, (const float *)d_shaped, NULL, 0, (float *)d_rep, 1, len_shaped, len_rep)); /* :607-612 */
+            srand(seed);
+        }
         for (int i = 0; i < n_snr; ++i) {                  /* SNR loop :1202-1222 */
             ofdm_rx_dump d;
             memset(&d, 0, sizeof d);
             d.bits = (uint32_t *)d_rx;
             CHECK(ofdm_memset_dev(ctx, d_cnt, 0, sizeof(ofdm_counters)));
+            if (full_chain) {
+                const int rx_start = rand() % (len_rep - len_cap);                                            /* :949 */
+                CHECK(ofdm_awgn_philox_len(ctx, (const float *)d_rep, NULL, SNR[i], seed, (uint32_t)i, 0, (float *)d_ota, 1, len_rep, mode));  /* :1208 */
+                CHECK(ofdm_gather(ctx, (const float *)d_ota, NULL, rx_start, (float *)d_cap, 1, len_rep, len_cap));                             /* :955 */
+                CHECK(ofdm_packet_detect(ctx, (const float *)d_cap, (float *)d_corr, 1, len_cap));            /* :972 */
+                CHECK(ofdm_packet_select(ctx, (const float *)d_corr, (int32_t *)d_idx, 1, len_cap - 47));     /* :978 */
+                CHECK(ofdm_rrc_rx_idx(ctx, (const float *)d_cap, (const int32_t *)d_idx, (float *)d_rxf, 1, len_cap, len480));  /* :965, :986-996 */
+                CHECK(ofdm_cfo_coarse(ctx, (const float *)d_rxf, (float *)d_c1, NULL, 1, len480));            /* :1004 */
+                CHECK(ofdm_cfo_fine(ctx, (const float *)d_c1, (float *)d_c2, NULL, 1, len480));               /* :1012 */
+                CHECK(ofdm_gather(ctx, (const float *)d_c2, NULL, 160, (float *)d_ld, 1, len480, len));
+                CHECK(ofdm_rx_frames(ctx, (const float *)d_ld, (const uint32_t *)d_bits, 1, n_sym, mode, (ofdm_counters *)d_cnt, &d));  /* :1018-1165 */
+            } else
             CHECK(ofdm_awgn_rx_philox(ctx, (const float *)d_frame, (const float *)d_power, (const uint32_t *)d_bits, SNR[i], seed,
                                       (uint32_t)i, 0, 1, n_sym, mode, (ofdm_counters *)d_cnt, &d));
             CHECK(ofdm_memcpy_d2h(ctx, &totals[i], d_cnt, sizeof(ofdm_counters)));
@@ -215,6 +249,10 @@ int main(int argc, char **argv)
                 decode_message(rx_words, n_bits, text);
                 printf("\n\nFor SNR = %lf \n\nReceived Message: \n%s\n", SNR[i], text);      /* :1204, :1177-1182 */
             }
+        }
+        if (full_chain) {
+            void *all[] = {d_f480, d_shaped, d_rep, d_ota, d_cap, d_corr, d_idx, d_rxf, d_c1, d_c2, d_ld};
+            for (unsigned k = 0; k < sizeof all / sizeof all[0]; ++k) ofdm_dev_free(ctx, all[k]);
         }
         ofdm_dev_free(ctx, d_bits); ofdm_dev_free(ctx, d_rx); ofdm_dev_free(ctx, d_frame);
         ofdm_dev_free(ctx, d_power); ofdm_dev_free(ctx, d_cnt);

@@ -197,6 +197,9 @@ int ofdm_rrc_tx(ofdm_ctx *ctx, const float *frames_dev, float *out_dev, long n_f
 int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in_dev, float *out_dev, long n_frames, int in_len, int packet_idx, int frame_len);
 int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx_dev, const float *g_dev, const float *power_dev, float snr_db,
                          float *ota_dev, long n_frames, int frame_len, int mode);
+/* same with on-chip Philox draws (domain 3: sample n of a frame takes normal n & 3 of block n >> 2) */
+int ofdm_awgn_philox_len(ofdm_ctx *ctx, const float *tx_dev, const float *power_dev, float snr_db, uint32_t seed, uint32_t stream,
+                         uint64_t frame0, float *ota_dev, long n_frames, int frame_len, int mode);
 
 /* ---- packet detection / selection, batched over n captures of len samples ----
  * ofdm_packet_detect: Packet_Detection, OFDM.c:659-683 (delay 16, window 32, no conjugate): corr_dev [n][len-47],
