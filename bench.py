@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1_000_000, help="frames per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=4000, help="frames in the single-thread CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="frames in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also measure configs[2] (streaming) and configs[3] (Philox MC)")
     ap.add_argument("--stream-frames", type=int, default=8_388_608, help="frames for the streaming extra (16 Mi data symbols)")
