@@ -170,3 +170,23 @@ def test_streaming_kernel_equals_generic_kernel(ofdm, pkg, port, mode):
         assert res[0][0].bit_errors == res[0][2].bit_errors
         if mode == pkg.MODE_EXACT:
             assert res[0][0].bit_errors == port.chain(bits, g, 2, 6.0).bit_errors
+
+
+@pytest.mark.parametrize("n_sym", [6, 37])
+def test_long_frames_generic_receiver(ofdm, pkg, port, n_sym):
+    """many symbols per frame: several passes of four windows, the last one partly empty (generic kernel)."""
+    n_frames = 40
+    bits, g = bits_and_noise(900 + n_sym, n_frames, n_sym)
+    packed = ofdm.to_dev(pkg.pack_bits_host(bits).view(np.int32))
+    gd = ofdm.to_dev(g)
+    frames, power = ofdm.tx_frames(packed, n_sym, pkg.MODE_EXACT)
+    assert same(frames.cpu().numpy(), port.tx_frames(bits, n_sym))
+    for snr in (4.0, 11.0):
+        acc, fe, fv = port.chain(bits, g, n_sym, snr, per_frame=True)
+        cnt, d = ofdm.awgn_rx_inject(frames, gd, packed, snr, n_sym, pkg.MODE_EXACT, power=power, want=("frame_bit_errors", "frame_evm_lin"))
+        assert same(d["frame_bit_errors"].cpu().numpy(), fe)
+        assert np.allclose(d["frame_evm_lin"].cpu().numpy(), fv, rtol=REL)
+        cnt2, _ = ofdm.awgn_rx_inject(frames, gd, packed, snr, n_sym, pkg.MODE_EXACT, power=power)      # no-dump path
+        assert (cnt2.bit_errors, cnt2.rail_errors, cnt2.frames_in_error) == (acc.bit_errors, acc.rail_errors, acc.frames_in_error)
+        cnt3, _ = ofdm.awgn_rx_inject(frames, gd, packed, snr, n_sym, pkg.MODE_FAST, power=power)
+        assert abs(int(cnt3.bit_errors) - int(acc.bit_errors)) <= 3
