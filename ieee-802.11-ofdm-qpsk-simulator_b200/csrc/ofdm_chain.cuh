@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
         // ---- SNR loop OFDM.c:1202: channel :635 + receiver :1018-1165 on the frame held in shared memory
         for (int si = 0; si < p.n_snr; ++si) {
             double sigma_d = 0.0; float sigma_f;
-            if (EXACT) { sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si])); sigma_f = (float)sigma_d; }
+            if (EXACT) { sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si])); sigma_f = (float)sigma_d; sigma_d = __dmul_rn(sigma_d, kTwScale); }
             else sigma_f = sqrtP * p.inv_sqrt_snr[si];
             float za[4], zb[4];
             philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)blk_base, kDomainNoise, za);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
             for (int i = 0; i < 8; ++i) {
                 const int m = slot_m<EXACT>(i);
                 float2 s = src[u + 8 * m];
-                s.x = add_noise<EXACT>(s.x, m < 4 ? za[m & 3] : zb[m & 3], sigma_d, sigma_f);
+                s.x = add_noise_s<EXACT>(s.x, m < 4 ? za[m & 3] : zb[m & 3], sigma_d, sigma_f);
                 r[i] = s;
             }
             fft64<EXACT>(r, tw, tile, u);
@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<EXACT, NOISE>()
             const uint32_t phase = (uint32_t)((k / kStages) & 1);
             const double sigma_d = NOISE != kNoiseNone ? __shfl_sync(0xffffffffu, sig_mine, kk) : 0.0;
             const float sigma_f = (float)sigma_d;
+            const double sigma_s = __dmul_rn(sigma_d, kTwScale);        // for add_noise_s
             // this frame's payload words for the lane's three items (used after the transform)
             const uint32_t *wb = p.tx_bits + f * 6;
             const uint32_t w0 = wb[ic.word[0]], w1 = wb[ic.word[1]], w2 = wb[ic.word[2]];
@@ -424,8 +425,8 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<EXACT, NOISE>()
             for (int i = 0; i < 8; ++i) {
                 const int m = slot_m<EXACT>(i);
                 float2 smp = ws.st[s].x[grp][u + 8 * m];
-                if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
-                if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
+                if (NOISE == kNoiseInject) smp.x = add_noise_s<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_s, sigma_f);
+                if (NOISE == kNoisePhilox) smp.x = add_noise_s<EXACT>(smp.x, z[m], sigma_s, sigma_f);
                 v[i] = smp;
             }
             __syncwarp();                                         // every lane has its samples: the stage can be refilled

@@ -29,6 +29,8 @@ constexpr double kTw64[32][2] = { OFDM_TWIDDLE64_TABLE };
 constexpr double kW8r = kTw64[8][0],   kW8i = kTw64[8][1];      // W_8^1
 constexpr double kW16r = kTw64[16][0], kW16i = kTw64[16][1];    // W_4^1 = W_8^2 (6.1e-17, -1): NOT special-cased
 constexpr double kW24r = kTw64[24][0], kW24i = kTw64[24][1];    // W_8^3
+constexpr double kW8rS = kTw64[8][0] * 0x1p896, kW8iS = kTw64[8][1] * 0x1p896;       // the same, pre-scaled for bf_exact_s
+constexpr double kW24rS = kTw64[24][0] * 0x1p896, kW24iS = kTw64[24][1] * 0x1p896;
 
 struct Tables {
     double2 tw64[32];       // exact twiddles
@@ -50,6 +52,28 @@ __device__ __forceinline__ int rev3(int v) { return ((v & 1) << 2) | (v & 2) | (
 __device__ __forceinline__ void bf_exact(float2 &e, float2 &o, double wr, double wi)
 {
     double c = (double)o.x, d = (double)o.y;
+    float wx = __double2float_rn(__dsub_rn(__dmul_rn(wr, c), __dmul_rn(wi, d)));
+    float wy = __double2float_rn(__dadd_rn(__dmul_rn(wr, d), __dmul_rn(wi, c)));
+    float2 a = e;
+    e.x = __fadd_rn(a.x, wx); e.y = __fadd_rn(a.y, wy);
+    o.x = __fsub_rn(a.x, wx); o.y = __fsub_rn(a.y, wy);
+}
+// float -> double without the XU pipe.  The float's bits are re-laid as a double with the SAME biased exponent
+// field, i.e. the value x * 2^-896 (exact for normals, denormals and zeros: a zero exponent field means
+// 0.m * 2^-1022 there and 0.m * 2^-126 here).  The missing 2^896 is folded into the twiddle, so the double product
+// W * x has the same real value and therefore the same rounding as the reference's.  (Non-finite samples are not
+// reproduced by this path.)
+constexpr double kTwScale = 0x1p896;
+__device__ __forceinline__ double f2d_scaled(float x)
+{
+    const uint32_t u = __float_as_uint(x);
+    const uint32_t hi = ((u << 1) >> 4) | (u & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(u << 29));
+}
+// same butterfly as bf_exact with pre-scaled twiddles (wr, wi already multiplied by 2^896)
+__device__ __forceinline__ void bf_exact_s(float2 &e, float2 &o, double wr, double wi)
+{
+    const double c = f2d_scaled(o.x), d = f2d_scaled(o.y);
     float wx = __double2float_rn(__dsub_rn(__dmul_rn(wr, c), __dmul_rn(wi, d)));
     float wy = __double2float_rn(__dadd_rn(__dmul_rn(wr, d), __dmul_rn(wi, c)));
     float2 a = e;
@@ -89,6 +113,10 @@ __device__ __forceinline__ TwExact load_tw_exact(int t)
     w.w32a = c_tab.tw64[2 * t];  w.w32b = c_tab.tw64[2 * t + 16];
     w.w64a = c_tab.tw64[t];      w.w64b = c_tab.tw64[t + 8];
     w.w64c = c_tab.tw64[t + 16]; w.w64d = c_tab.tw64[t + 24];
+    // pre-scaled by 2^896 for bf_exact_s (exact: a power of two, no overflow for |w| <= 1)
+    double2 *all[7] = {&w.w16, &w.w32a, &w.w32b, &w.w64a, &w.w64b, &w.w64c, &w.w64d};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { all[i]->x = __dmul_rn(all[i]->x, kTwScale); all[i]->y = __dmul_rn(all[i]->y, kTwScale); }
     return w;
 }
 
@@ -101,9 +129,9 @@ __device__ __forceinline__ void fft64_exact(float2 (&v)[8], const TwExact &tw, f
     bf_unit(v[0], v[2]); bf_quarter(v[1], v[3]);
     bf_unit(v[4], v[6]); bf_quarter(v[5], v[7]);
     bf_unit(v[0], v[4]);
-    bf_exact(v[1], v[5], kW8r, kW8i);
+    bf_exact_s(v[1], v[5], kW8rS, kW8iS);
     bf_quarter(v[2], v[6]);
-    bf_exact(v[3], v[7], kW24r, kW24i);
+    bf_exact_s(v[3], v[7], kW24rS, kW24iS);
     // 8x8 transpose: position q = 8*rev3(u) + i  ->  lane q%8, slot q/8
     const int row = rev3(u) * 9;
 #pragma unroll
@@ -113,12 +141,12 @@ __device__ __forceinline__ void fft64_exact(float2 (&v)[8], const TwExact &tw, f
     for (int j = 0; j < 8; ++j) v[j] = tile[j * 9 + u];
     __syncwarp();
     // sz = 16, 32, 64 on positions u + 8j
-    bf_exact(v[0], v[1], tw.w16.x, tw.w16.y); bf_exact(v[2], v[3], tw.w16.x, tw.w16.y);
-    bf_exact(v[4], v[5], tw.w16.x, tw.w16.y); bf_exact(v[6], v[7], tw.w16.x, tw.w16.y);
-    bf_exact(v[0], v[2], tw.w32a.x, tw.w32a.y); bf_exact(v[1], v[3], tw.w32b.x, tw.w32b.y);
-    bf_exact(v[4], v[6], tw.w32a.x, tw.w32a.y); bf_exact(v[5], v[7], tw.w32b.x, tw.w32b.y);
-    bf_exact(v[0], v[4], tw.w64a.x, tw.w64a.y); bf_exact(v[1], v[5], tw.w64b.x, tw.w64b.y);
-    bf_exact(v[2], v[6], tw.w64c.x, tw.w64c.y); bf_exact(v[3], v[7], tw.w64d.x, tw.w64d.y);
+    bf_exact_s(v[0], v[1], tw.w16.x, tw.w16.y); bf_exact_s(v[2], v[3], tw.w16.x, tw.w16.y);
+    bf_exact_s(v[4], v[5], tw.w16.x, tw.w16.y); bf_exact_s(v[6], v[7], tw.w16.x, tw.w16.y);
+    bf_exact_s(v[0], v[2], tw.w32a.x, tw.w32a.y); bf_exact_s(v[1], v[3], tw.w32b.x, tw.w32b.y);
+    bf_exact_s(v[4], v[6], tw.w32a.x, tw.w32a.y); bf_exact_s(v[5], v[7], tw.w32b.x, tw.w32b.y);
+    bf_exact_s(v[0], v[4], tw.w64a.x, tw.w64a.y); bf_exact_s(v[1], v[5], tw.w64b.x, tw.w64b.y);
+    bf_exact_s(v[2], v[6], tw.w64c.x, tw.w64c.y); bf_exact_s(v[3], v[7], tw.w64d.x, tw.w64d.y);
 }
 
 // ---------------------------------------------------------------- fast-mode fp32 transform

@@ -231,6 +231,13 @@ __device__ __forceinline__ float add_noise(float xr, float g, double sigma_d, fl
     if constexpr (EXACT) return __fadd_rn(xr, __double2float_rn(__dmul_rn(sigma_d, (double)g)));
     else return fmaf(sigma_f, g, xr);
 }
+// the same with sigma pre-scaled by 2^896 and the draw widened without the XU pipe (see f2d_scaled): identical bits
+template <bool EXACT>
+__device__ __forceinline__ float add_noise_s(float xr, float g, double sigma_scaled, float sigma_f)
+{
+    if constexpr (EXACT) return __fadd_rn(xr, __double2float_rn(__dmul_rn(sigma_scaled, f2d_scaled(g))));
+    else return fmaf(sigma_f, g, xr);
+}
 
 // Philox noise for buffers that are not LTS||data frames (e.g. the oversampled, repeated waveform): consecutive
 // quadruples of samples share a block, domain 3.  One thread per block of four samples.
