@@ -425,8 +425,8 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<EXACT, NOISE>()
             for (int i = 0; i < 8; ++i) {
                 const int m = slot_m<EXACT>(i);
                 float2 smp = ws.st[s].x[grp][u + 8 * m];
-                if (NOISE == kNoiseInject) smp.x = add_noise_s<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_s, sigma_f);
-                if (NOISE == kNoisePhilox) smp.x = add_noise_s<EXACT>(smp.x, z[m], sigma_s, sigma_f);
+                if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
+                if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
                 v[i] = smp;
             }
             __syncwarp();                                         // every lane has its samples: the stage can be refilled

@@ -114,9 +114,12 @@ __device__ __forceinline__ TwExact load_tw_exact(int t)
     w.w64a = c_tab.tw64[t];      w.w64b = c_tab.tw64[t + 8];
     w.w64c = c_tab.tw64[t + 16]; w.w64d = c_tab.tw64[t + 24];
     // pre-scaled by 2^896 for bf_exact_s (exact: a power of two, no overflow for |w| <= 1)
-    double2 *all[7] = {&w.w16, &w.w32a, &w.w32b, &w.w64a, &w.w64b, &w.w64c, &w.w64d};
+    // The exact butterflies are bound by the XU pipe (F2F) on one side and by instruction issue on the other: widening
+    // on the ALU costs four instructions instead of one.  Measured optimum on B200: stages 32 and 64 widen on the ALU
+    // (their twiddles carry the 2^896), the in-lane stages and stage 16 keep F2F.
+    double2 *all[6] = {&w.w32a, &w.w32b, &w.w64a, &w.w64b, &w.w64c, &w.w64d};
 #pragma unroll
-    for (int i = 0; i < 7; ++i) { all[i]->x = __dmul_rn(all[i]->x, kTwScale); all[i]->y = __dmul_rn(all[i]->y, kTwScale); }
+    for (int i = 0; i < 6; ++i) { all[i]->x = __dmul_rn(all[i]->x, kTwScale); all[i]->y = __dmul_rn(all[i]->y, kTwScale); }
     return w;
 }
 
@@ -129,9 +132,9 @@ __device__ __forceinline__ void fft64_exact(float2 (&v)[8], const TwExact &tw, f
     bf_unit(v[0], v[2]); bf_quarter(v[1], v[3]);
     bf_unit(v[4], v[6]); bf_quarter(v[5], v[7]);
     bf_unit(v[0], v[4]);
-    bf_exact_s(v[1], v[5], kW8rS, kW8iS);
+    bf_exact(v[1], v[5], kW8r, kW8i);              // the in-lane stages keep the XU conversion: the two pipes share the load
     bf_quarter(v[2], v[6]);
-    bf_exact_s(v[3], v[7], kW24rS, kW24iS);
+    bf_exact(v[3], v[7], kW24r, kW24i);
     // 8x8 transpose: position q = 8*rev3(u) + i  ->  lane q%8, slot q/8
     const int row = rev3(u) * 9;
 #pragma unroll
@@ -141,8 +144,8 @@ __device__ __forceinline__ void fft64_exact(float2 (&v)[8], const TwExact &tw, f
     for (int j = 0; j < 8; ++j) v[j] = tile[j * 9 + u];
     __syncwarp();
     // sz = 16, 32, 64 on positions u + 8j
-    bf_exact_s(v[0], v[1], tw.w16.x, tw.w16.y); bf_exact_s(v[2], v[3], tw.w16.x, tw.w16.y);
-    bf_exact_s(v[4], v[5], tw.w16.x, tw.w16.y); bf_exact_s(v[6], v[7], tw.w16.x, tw.w16.y);
+    bf_exact(v[0], v[1], tw.w16.x, tw.w16.y); bf_exact(v[2], v[3], tw.w16.x, tw.w16.y);
+    bf_exact(v[4], v[5], tw.w16.x, tw.w16.y); bf_exact(v[6], v[7], tw.w16.x, tw.w16.y);
     bf_exact_s(v[0], v[2], tw.w32a.x, tw.w32a.y); bf_exact_s(v[1], v[3], tw.w32b.x, tw.w32b.y);
     bf_exact_s(v[4], v[6], tw.w32a.x, tw.w32a.y); bf_exact_s(v[5], v[7], tw.w32b.x, tw.w32b.y);
     bf_exact_s(v[0], v[4], tw.w64a.x, tw.w64a.y); bf_exact_s(v[1], v[5], tw.w64b.x, tw.w64b.y);
