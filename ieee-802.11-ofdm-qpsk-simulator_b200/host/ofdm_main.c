@@ -15,6 +15,7 @@
  *       random capture window, packet detection / selection, matched filter + decimation, coarse + fine CFO,
  *       then the stage chain), OFDM.c:467-618 and :941-1165; --stage-chain keeps only the stage chain;
  *   --frames N (N > 1): N frames of Philox random bits per SNR point through the fused Monte-Carlo kernel.
+ *   --taps L (with --frames N): configs[4], per-frame random multipath channel with L <= 16 taps in front of the noise;
  *   --gpus N: the frames of the Monte-Carlo sweep are sharded across N GPUs of this node by global frame index
  *       (one context per GPU, all driven from this thread) and the counters are summed with ONE NCCL all-reduce
  *       per buffer type (built with -DOFDM_WITH_NCCL; link -lnccl).
@@ -81,7 +82,7 @@ static void decode_message(const uint32_t *words, int n_bits, char *out)
     } while (0)
 
 /* shard (frame range) across GPUs, counter-based RNG keyed on the global frame index, one all-reduce */
-static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, const float *SNR, int n_snr, int mode, ofdm_counters *totals)
+static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, int n_taps, const float *SNR, int n_snr, int mode, ofdm_counters *totals)
 {
     ofdm_ctx *ctxs[8] = {0};
     ofdm_ctx *ctx = NULL;
@@ -103,7 +104,8 @@ static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, co
         long base = frames / n_gpus, rem = frames % n_gpus;
         long lo = d * base + (d < rem ? d : rem), n = base + (d < rem ? 1 : 0);
         ctx = ctxs[d];
-        CHECK(ofdm_mc_sweep_philox_dev(ctx, seed, (uint64_t)lo, n, n_sym, SNR, n_snr, mode, (ofdm_counters *)cnt[d]));
+        if (n_taps > 0) CHECK(ofdm_mc_sweep_multipath_dev(ctx, seed, (uint64_t)lo, n, n_sym, n_taps, SNR, n_snr, mode, (ofdm_counters *)cnt[d]));
+        else CHECK(ofdm_mc_sweep_philox_dev(ctx, seed, (uint64_t)lo, n, n_sym, SNR, n_snr, mode, (ofdm_counters *)cnt[d]));
         CHECK(ofdm_counters_pack(ctx, (const ofdm_counters *)cnt[d], n_snr, (uint64_t *)ints[d], (double *)dbls[d]));
     }
     NCHECK(ncclGroupStart());
@@ -133,7 +135,7 @@ int main(int argc, char **argv)
     const char *message = "Hey! I am Vivaswan";          /* OFDM.c:20 */
     const char *outdir = "data", *dump = NULL;
     long frames = 1;
-    int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0, n_gpus = 1, full_chain = 1;
+    int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0, n_gpus = 1, full_chain = 1, n_taps = 0;
     float snr_start = 6.0f, snr_step = 1.0f;             /* OFDM.c:18, :1195-1198 */
     unsigned seed = 1;
     for (int i = 1; i < argc; ++i) {
@@ -151,6 +153,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--seed")) seed = (unsigned)strtoul(v, NULL, 10);
         else if (!strcmp(a, "--device")) device = atoi(v);
         else if (!strcmp(a, "--gpus")) n_gpus = atoi(v);
+        else if (!strcmp(a, "--taps")) n_taps = atoi(v);
         else if (!strcmp(a, "--outdir")) outdir = v;
         else if (!strcmp(a, "--dump")) dump = v;
         else if (!strcmp(a, "--mode")) mode = !strcmp(v, "fast") ? OFDM_MODE_FAST : OFDM_MODE_EXACT;
@@ -167,7 +170,7 @@ int main(int argc, char **argv)
     if (n_gpus > 1) {
 #ifdef OFDM_WITH_NCCL
         if (frames < 2) { fprintf(stderr, "--gpus needs --frames N > 1\n"); return 2; }
-        int rc = sweep_multi_gpu(n_gpus, seed, frames, n_sym, SNR, n_snr, mode, totals);
+        int rc = sweep_multi_gpu(n_gpus, seed, frames, n_sym, n_taps, SNR, n_snr, mode, totals);
         if (rc) return rc;
 #else
         fprintf(stderr, "built without NCCL (make ofdm_sweep NCCL=1)\n");
@@ -178,6 +181,14 @@ int main(int argc, char **argv)
 
     if (n_gpus > 1) {
         /* totals already hold the all-reduced counters */
+    } else if (frames > 1 && n_taps > 0) {             /* configs[4]: per-frame random multipath taps */
+        void *d_cnt = NULL;
+        CHECK(ofdm_dev_alloc(ctx, &d_cnt, sizeof(ofdm_counters) * (size_t)n_snr));
+        CHECK(ofdm_memset_dev(ctx, d_cnt, 0, sizeof(ofdm_counters) * (size_t)n_snr));
+        CHECK(ofdm_mc_sweep_multipath_dev(ctx, seed, 0, frames, n_sym, n_taps, SNR, n_snr, mode, (ofdm_counters *)d_cnt));
+        CHECK(ofdm_memcpy_d2h(ctx, totals, d_cnt, sizeof(ofdm_counters) * (size_t)n_snr));
+        CHECK(ofdm_ctx_sync(ctx));
+        ofdm_dev_free(ctx, d_cnt);
     } else if (frames > 1) {
         CHECK(ofdm_mc_sweep_philox(ctx, seed, 0, frames, n_sym, SNR, n_snr, mode, totals));
     } else {

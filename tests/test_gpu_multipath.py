@@ -60,3 +60,18 @@ def test_philox_taps_and_sweep(ofdm, pkg, port):
     b1 = ofdm.mc_sweep_multipath(seed, 400, 600, n_sym, n_taps, snrs, pkg.MODE_EXACT)
     for x, y, z in zip(a, b0, b1):
         assert x.bit_errors == y.bit_errors + z.bit_errors and x.frames == 1000
+
+
+def test_c_driver_multipath_sweep(tmp_path):
+    """configs[4] through the C host driver (EVM vs SNR file): EVM falls with SNR, BER has the fading floor."""
+    import os, subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "ieee-802.11-ofdm-qpsk-simulator_b200", "ofdm_sweep")
+    out = tmp_path / "data"; out.mkdir()
+    r = subprocess.run([exe, "--quiet", "--outdir", str(out), "--frames", "100000", "--taps", "8", "--snr-start", "5", "--snr-count", "8",
+                        "--snr-step", "5", "--mode", "fast"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ber = [float(w) for w in open(out / "Output_BER.txt").read().split()]
+    evm = [float(w) for w in open(out / "Output_EVM_AGC.txt").read().split()]
+    assert len(ber) == 8 and all(a >= b for a, b in zip(ber, ber[1:])) and ber[0] > 0.05 and 0 < ber[-1] < ber[0] / 10
+    assert all(np.isfinite(e) for e in evm)
