@@ -114,8 +114,10 @@ SIGNATURES = {
 }
 
 
-def load_library(path=LIB_PATH):
-    """dlopen the C-ABI library and attach the prototypes.  Raises if the library is not built."""
+def load_library(path=None):
+    """dlopen the C-ABI library and attach the prototypes.  Raises if the library is not built.
+    OFDM_B200_LIB overrides the path (A/B runs of two builds on the same box)."""
+    path = path or os.environ.get("OFDM_B200_LIB") or LIB_PATH
     if not os.path.exists(path):
         raise OfdmError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)" % path)

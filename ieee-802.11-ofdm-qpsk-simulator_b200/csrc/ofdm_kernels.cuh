@@ -359,8 +359,8 @@ __device__ __forceinline__ uint32_t process_bin_full(float2 F, float2 Hh, float 
 //
 // EXACT: the decision the reference takes is the sign of float(num/den) (:1050, :860).  For normal
 // magnitudes that is the sign of the exact numerator a*c+b*d (resp. b*c-a*d).  Its fp32 evaluation
-// errs by < 2^-23 m, m = (|a|+|b|)(|c|+|d|), and is trusted only above 1e-6 m, with m in
-// [1e-20, 1e15] and den < 1e15 so that neither the products nor the float quotient can underflow;
+// errs by < 2^-23 m, m = (|a|+|b|)(|c|+|d|), and is trusted only above max(1e-6 m, 1e-30) (which also keeps m >= 1e-30,
+// so denormal products cannot matter) with den < 1e14 (the float quotient then stays above the denormal range);
 // every other case (about 1e-6 of the bins, plus degenerate frames) takes the exact double-widened
 // division.  The EVM term uses the fp32 quotient (1e-5 contract).
 template <bool EXACT>
@@ -375,8 +375,10 @@ __device__ __forceinline__ uint32_t process_bin_hot(float2 F, float2 Hh, float s
     const uint32_t sq = txp << 31, sx = (txp ^ (txp >> 1)) << 31;          // IEEE sign bits of the tx Q / I rails
     uint32_t ei_ = (__float_as_uint(sr) ^ sx) >> 31, eq_ = (__float_as_uint(si) ^ sq) >> 31;
     if (EXACT) {
+        // |num| > max(1e-6 m, 1e-30) also bounds m from below (|num| <= m), den < 1e14 keeps the float quotient above the
+        // denormal range; non-finite m or den fail the comparisons.
         const float m = (fabsf(a) + fabsf(b)) * (fabsf(c) + fabsf(d));
-        const bool safe = fminf(fabsf(sr), fabsf(si)) > 1e-6f * m && m > 1e-20f && fmaxf(m, den) < 1e15f;
+        const bool safe = fminf(fabsf(sr), fabsf(si)) > fmaxf(1e-6f * m, 1e-30f) && den < 1e14f;
         if (!safe && valid) {
             const float2 E = div_exact(F, Hh, sc);
             ex = E.x; ey = E.y;
