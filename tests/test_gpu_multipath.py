@@ -67,6 +67,9 @@ def test_c_driver_multipath_sweep(tmp_path):
     import os, subprocess
     from conftest import ROOT
     exe = os.path.join(ROOT, "ieee-802.11-ofdm-qpsk-simulator_b200", "ofdm_sweep")
+    if not os.path.exists(exe):
+        import __graft_entry__ as entry
+        entry.build()
     out = tmp_path / "data"; out.mkdir()
     r = subprocess.run([exe, "--quiet", "--outdir", str(out), "--frames", "100000", "--taps", "8", "--snr-start", "5", "--snr-count", "8",
                         "--snr-step", "5", "--mode", "fast"], capture_output=True, text=True, timeout=300)
