@@ -20,7 +20,8 @@
  * Pointers documented "device" are CUDA device pointers (from ofdm_dev_alloc or any CUDA
  * allocator, e.g. a torch tensor's data_ptr); "host" pointers are ordinary memory.  All device
  * work is enqueued on the context's stream; entry points that return results to host memory
- * synchronise that stream before returning.  There is no CPU fallback anywhere.
+ * synchronise that stream before returning.  There is no CPU fallback anywhere.  An ofdm_ctx is bound to one GPU and is
+ * not thread-safe: use one context per host thread (or per GPU, as host/ofdm_main.c does for its multi-GPU sweep).
  *
  * mode: OFDM_MODE_EXACT reproduces the reference's arithmetic bit for bit (double twiddle
  * products rounded to float, float add/sub, double-widened complex division; SURVEY.md
