@@ -10,7 +10,8 @@ TX, the channel and RX at one SNR point: symbols/step = frames x n_sym x n_snr.
   value   inputs resident in HBM, CUDA-event timed on the launching stream
   e2e     the same sweep through ofdm_sweep_inject_host: HOST (pinned) bits + draws, H2D copies,
           kernels and the D2H of the counters inside the timed region
-  roofline  dominant kernel k_stream_rx2<exact,inject>: algorithmic bytes (3100 B per frame and SNR
+  roofline  dominant kernel k_stream_rx2<checked,inject> (EXACT mode: fp32 speculation, verified, doubtful
+            frames replayed in the reference's arithmetic): algorithmic bytes (3100 B per frame and SNR
             point) / mean launch time (CUDA events around each launch in the timed region)
   cpu_baseline  the compiled reference (oracle/_ref) stage chain on a bounded sample, one thread
 
@@ -287,6 +288,7 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     launches0 = o.launch_count
+    o.replayed_frames(reset=True)
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     all_evs = []
@@ -295,6 +297,7 @@ def run_gpu(args):
     t1.record()
     barrier()
     launches = o.launch_count - launches0
+    replayed = o.replayed_frames() / max(1, args.steps)
     ms_total = t0.elapsed_time(t1)
     kernel_ms = [a.elapsed_time(b) for a, b in all_evs]
     resident_counts = o.read_counters(host_cnt)
@@ -334,7 +337,7 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("k_stream_rx2_exact_inject_bytes_per_launch")
+                traffic = json.load(f).get("k_stream_rx2_checked_inject_bytes_per_launch")
                 if traffic is not None and n_frames != 1_000_000:
                     traffic = traffic * n_frames / 1_000_000        # captured on the 1 M-frame launch
         ber = [c.bit_errors / max(1, c.bits) for c in resident_counts]
@@ -346,13 +349,17 @@ def run_gpu(args):
                                                    % (g.numel() * 4 / 1e9, frames.numel() * 4 / 1e9),
                            "parallelism": "frames sharded across %d GPU(s), one NCCL all-reduce of the counters" % world},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_total / args.steps,
-                        "h2d_bytes_per_step": int(bits_h.numel() * 4 + g_h.numel() * 4),
+                        # the draws of the guard interval / cyclic prefixes are never read by the receiver and stay on the host
+                        "h2d_bytes_per_step": int(bits_h.numel() * 4 + n_frames * (128 + 64 * N_SYM) * 4),
+                        "host_buffer_bytes": int(bits_h.numel() * 4 + g_h.numel() * 4),
                         "d2h_bytes_per_step": int(n_snr * pkg.COUNTERS_BYTES)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_stream_rx2<exact,inject>", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "k_stream_rx2<checked,inject>", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "bytes_per_launch": BYTES_PER_FRAME_PASS * n_frames, "kernel_ms": k_ms,
-                             "kernel_share_of_step": k_ms * n_snr / ms_step},
+                             "kernel_share_of_step": k_ms * n_snr / ms_step,
+                             "frames_replayed_exactly_per_sweep": replayed,
+                             "frames_per_sweep": n_frames * n_snr},
                 "clocks": clocks,
                 "ber_0_10_20dB": [ber[0], ber[10], ber[20]]}
         if extras:

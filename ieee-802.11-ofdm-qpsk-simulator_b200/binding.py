@@ -62,6 +62,7 @@ SIGNATURES = {
     "ofdm_ctx_stream": (_VP, [_VP]),
     "ofdm_ctx_sync": (_I, [_VP]),
     "ofdm_ctx_set_option": (_I, [_VP, C.c_char_p, _I]),
+    "ofdm_ctx_replayed_frames": (_I, [_VP, C.POINTER(_U64), _I]),
     "ofdm_ctx_sm_count": (_I, [_VP]),
     "ofdm_ctx_launch_count": (_U64, [_VP]),
     "ofdm_dev_alloc": (_I, [_VP, C.POINTER(_VP), _SZ]),
@@ -164,6 +165,12 @@ class Ofdm:
 
     def set_option(self, name, value):
         self._check(self.lib.ofdm_ctx_set_option(self.h, name.encode(), int(value)))
+
+    def replayed_frames(self, reset=False):
+        """frames the speculating EXACT kernels replayed in the reference's arithmetic (process-wide counter)"""
+        v = _U64(0)
+        self._check(self.lib.ofdm_ctx_replayed_frames(self.h, C.byref(v), int(bool(reset))))
+        return int(v.value)
 
     def sync(self):
         self._check(self.lib.ofdm_ctx_sync(self.h))

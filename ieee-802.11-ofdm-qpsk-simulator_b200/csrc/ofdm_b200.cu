@@ -19,6 +19,8 @@ struct ofdm_ctx {
     cudaEvent_t copy_done[2] = {nullptr, nullptr}, call_start = nullptr;
     uint64_t launches = 0;
     bool force_generic = false;      // testing knob: route n_sym == 2 sweeps through the generic kernel too
+    bool checked = true;             // EXACT sweeps speculate in fp32, verify, and replay exactly (kArithChecked)
+    bool force_replay = false;       // testing knob: the verification fails every frame
     char err[256] = {0};
     float lts_freq[128];
     float lts_time[320];
@@ -165,10 +167,10 @@ int launch_rx_d(ofdm_ctx *ctx, bool dump, const RxParams &p)
     return dump ? launch_rx<EXACT, NOISE, true>(ctx, p) : launch_rx<EXACT, NOISE, false>(ctx, p);
 }
 
-template <bool EXACT, int NOISE>
+template <int ARITH, int NOISE>
 int launch_stream(ofdm_ctx *ctx, const RxParams &p)
 {
-    auto k = k_stream_rx2<EXACT, NOISE>;
+    auto k = k_stream_rx2<ARITH, NOISE>;
     const size_t smem = stream_smem_bytes<NOISE>();
     OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
@@ -184,13 +186,20 @@ int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
     const bool aligned = ((uintptr_t)p.in % 16 == 0) && (noise != kNoiseInject || (uintptr_t)p.g % 16 == 0);
     if (!dump && p.n_sym == 2 && aligned && !ctx->force_generic) {
         if (mode == OFDM_MODE_EXACT) {
-            if (noise == kNoiseNone) return launch_stream<true, kNoiseNone>(ctx, p);
-            if (noise == kNoiseInject) return launch_stream<true, kNoiseInject>(ctx, p);
-            return launch_stream<true, kNoisePhilox>(ctx, p);
+            // fp32 speculation + verification + exact replay: same counts as the all-exact kernel (ofdm_chain.cuh)
+            if (ctx->checked && noise != kNoisePhilox) {
+                RxParams q = p;
+                q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+                if (noise == kNoiseNone) return launch_stream<kArithChecked, kNoiseNone>(ctx, q);
+                return launch_stream<kArithChecked, kNoiseInject>(ctx, q);
+            }
+            if (noise == kNoiseNone) return launch_stream<kArithExact, kNoiseNone>(ctx, p);
+            if (noise == kNoiseInject) return launch_stream<kArithExact, kNoiseInject>(ctx, p);
+            return launch_stream<kArithExact, kNoisePhilox>(ctx, p);
         }
-        if (noise == kNoiseNone) return launch_stream<false, kNoiseNone>(ctx, p);
-        if (noise == kNoiseInject) return launch_stream<false, kNoiseInject>(ctx, p);
-        return launch_stream<false, kNoisePhilox>(ctx, p);
+        if (noise == kNoiseNone) return launch_stream<kArithFast, kNoiseNone>(ctx, p);
+        if (noise == kNoiseInject) return launch_stream<kArithFast, kNoiseInject>(ctx, p);
+        return launch_stream<kArithFast, kNoisePhilox>(ctx, p);
     }
     if (mode == OFDM_MODE_EXACT) {
         if (noise == kNoiseNone) return launch_rx_d<true, kNoiseNone>(ctx, dump, p);
@@ -344,7 +353,20 @@ int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value)
 {
     if (!ctx || !name) return OFDM_ERR_INVALID;
     if (!strcmp(name, "force_generic_rx")) { ctx->force_generic = value != 0; return OFDM_OK; }
+    if (!strcmp(name, "exact_speculation")) { ctx->checked = value != 0; return OFDM_OK; }
+    if (!strcmp(name, "force_replay")) { ctx->force_replay = value != 0; return OFDM_OK; }
     return fail(ctx, OFDM_ERR_INVALID, "unknown option");
+}
+int ofdm_ctx_replayed_frames(ofdm_ctx *ctx, uint64_t *count, int reset)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, count != nullptr);
+    unsigned long long v = 0;
+    OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    OFDM_CUDA(ctx, cudaMemcpyFromSymbol(&v, g_replayed_frames, sizeof v));
+    *count = v;
+    if (reset) { v = 0; OFDM_CUDA(ctx, cudaMemcpyToSymbol(g_replayed_frames, &v, sizeof v)); }
+    return OFDM_OK;
 }
 int ofdm_ctx_sm_count(const ofdm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t ofdm_ctx_launch_count(const ofdm_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -647,13 +669,25 @@ int ofdm_sweep_inject_host(ofdm_ctx *ctx, const uint32_t *bits_host, const float
     OFDM_CUDA(ctx, cudaEventRecord(ctx->call_start, ctx->stream));
     OFDM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->call_start, 0));
     OFDM_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(ofdm_counters) * (size_t)n_snr, ctx->stream));
-    const long chunk = 131072;
+    const long chunk = 65536;
     int c = 0;
     for (long f0 = 0; f0 < n_frames; f0 += chunk, ++c) {
         const long n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         char *db = (char *)bits + f0 * bits_per_frame, *dg = (char *)g + f0 * g_per_frame;
         OFDM_CUDA(ctx, cudaMemcpyAsync(db, (const char *)bits_host + f0 * bits_per_frame, n * bits_per_frame, cudaMemcpyHostToDevice, ctx->copy_stream));
-        OFDM_CUDA(ctx, cudaMemcpyAsync(dg, (const char *)g_host + f0 * g_per_frame, n * g_per_frame, cudaMemcpyHostToDevice, ctx->copy_stream));
+        const char *hg = (const char *)g_host + f0 * g_per_frame;
+        if (n_sym <= 4) {
+            // The receiver never reads the draws of the guard interval and the cyclic prefixes (Channel_Estimation :837-838
+            // and the CP strip :1028 skip those samples), so they stay on the host: strided copies of the LTS halves and of
+            // each symbol body -- 20 % fewer bytes over PCIe for the default frame.  The device buffer keeps the full layout.
+            OFDM_CUDA(ctx, cudaMemcpy2DAsync(dg + 32 * 4, g_per_frame, hg + 32 * 4, g_per_frame, 128 * 4, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+            for (int sy = 0; sy < n_sym; ++sy) {
+                const size_t off = (size_t)(160 + 80 * sy + 16) * 4;
+                OFDM_CUDA(ctx, cudaMemcpy2DAsync(dg + off, g_per_frame, hg + off, g_per_frame, 64 * 4, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+        } else {
+            OFDM_CUDA(ctx, cudaMemcpyAsync(dg, hg, n * g_per_frame, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
         OFDM_CUDA(ctx, cudaEventRecord(ctx->copy_done[c & 1], ctx->copy_stream));
         OFDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[c & 1], 0));
         float *fr = (float *)frames + f0 * len * 2, *pw = (float *)power + f0;

@@ -327,14 +327,121 @@ template <bool WITH_DRAWS> struct alignas(16) StreamWarp {
     float2 lts[2][kWin];
     StreamStage<WITH_DRAWS> st[kStages];
     uint64_t bar[kStages];
+    float radius[4];                // kArithChecked: error radius of each window's transform (see below)
 };
+// ---- arithmetic of the streaming receiver -------------------------------------------------------
+//   kArithFast     fp32 transform, fp32 channel, fp32 decisions
+//   kArithExact    the reference's arithmetic everywhere (ofdm_device.cuh, EXACT mode)
+//   kArithChecked  what OFDM_MODE_EXACT runs for the sweep: channel in the reference's arithmetic (so the
+//                  noisy time samples are the reference's bit for bit), transform and decisions speculated in
+//                  fp32, every decision verified against a rigorous bound on |fp32 path - reference path|,
+//                  and the whole frame replayed in the reference's arithmetic when any of its 192 rail
+//                  decisions is not provably the reference's.  Error counts are therefore exactly those of
+//                  kArithExact; the EVM sums differ by fp32 rounding (1e-5 contract), as they already do there.
+//
+// The bound.  Both transforms compute the same DFT of the same 64 floats x.  A radix-2 stage maps an error vector
+// with norm growth sqrt(2) and adds a local error of at most (eps_mul + u) |v_out|_2, u = 2^-24; |v_out|_2 after
+// stage s is 2^(s/2) |x|_2, so six stages give  |err|_2 <= 6 (eps_mul + u) 8 |x|_2.  Reference (OFDM.c:282-312:
+// double twiddle, product rounded to float, float add): eps_mul <= u(1 + 2^-26), i.e. <= 97 u |x|_2.  fp32 path
+// (dft8, float twiddles, FMA complex multiply, dft8): eps_mul <= 4u for a non-trivial factor, plus the separate
+// twiddle stage: <= (6*5 + 4) 8 u |x|_2 = 272 u |x|_2.  The channel estimate adds the rounding of A + B (:848):
+// <= 2u |A + B| <= 32 u max(|x_A|_2, |x_B|_2).  Every bin of a window is therefore within
+//      radius = kRadius * |x|_2,   kRadius = 512 u  (>= 97 + 272 + 32 = 401, the rest is margin for the
+// second-order terms, the approximate square root and the rounding of the threshold itself)
+// of the reference's value, for F, and (radius_A + radius_B)/2 for H.  With F = F~ + dF, H = H~ + dH the numerator
+// of the equaliser (:1050) moves by at most |dF| |H|_1 + |dH| |F|_1 + |dF||dH|, and its fp32 evaluation errs by
+// 2^-23 |F|_1 |H|_1 more (process_bin_hot).  The decision (:860-868) is the sign of the reference's numerator
+// whenever the quotient cannot underflow, which the magnitude guards below ensure.
+enum { kArithFast = 0, kArithExact = 1, kArithChecked = 2 };
+constexpr float kRadius = 512.f * 5.9604645e-8f;
+
+__device__ unsigned long long g_replayed_frames;     // frames the checked kernels replayed exactly (statistics)
+
+// radius of one window from the lane's share of sum |x|^2; windows whose energy is outside [1e-30, 1e20] are never
+// trusted (squares may have underflowed / the magnitude guards of the decision would not hold)
+__device__ __forceinline__ float window_radius(float n2, float scale)
+{
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(n2));
+    return (n2 >= 1e-30f && n2 < 1e20f) ? scale * r : __int_as_float(0x7f800000);
+}
+
+// One data bin, speculated: like process_bin_hot<false>, and reports whether both rail decisions are provably the
+// reference's.  rF / rH: error radii of F and H.  den_min: bins whose |H|^2 is below it are not trusted either --
+// not for the decisions but for the EVM sum, which at low SNR is dominated by the few bins with a tiny estimate
+// (|E|^2 ~ 1/|H|^2), where the fp32 transform's error in H would show: with |H| >= kEvmGuard radii the relative
+// error of an accepted quotient stays below ~2e-6 (the bound is about 300x the typical error).
+constexpr float kEvmGuard = 2048.f;
+__device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 Hh, uint32_t txp, float rF, float rH, float den_min, float &e2, bool &doubt)
+{
+    const float a = F.x, b = F.y, c = Hh.x, d = Hh.y;
+    const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
+    const float den = fmaf(c, c, d * d);
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+    const float ex = sr * inv, ey = si * inv;
+    const uint32_t sq = txp << 31, sx = (txp ^ (txp >> 1)) << 31;          // IEEE sign bits of the tx Q / I rails
+    const uint32_t ei_ = (__float_as_uint(sr) ^ sx) >> 31, eq_ = (__float_as_uint(si) ^ sq) >> 31;
+    const float fa = fabsf(a) + fabsf(b), hc = fabsf(c) + fabsf(d);
+    const float thr = fmaf(rF, hc + rH, fmaf(rH, fa, 1.2e-7f * (fa * hc)));
+    // reference numerator >= 1e-30 in magnitude and reference |H|^2 < 1e14: the float quotient keeps its sign (>= 1e-44)
+    const bool safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 1e-30f && den < 4e13f && den > den_min;
+    doubt = doubt || !safe;
+    const float er = ex - __uint_as_float(0x3F3504F3u | sx), eim = ey - __uint_as_float(0x3F3504F3u | sq);
+    e2 += fmaf(er, er, eim * eim);
+    return ei_ | (eq_ << 8) | ((ei_ & eq_) << 16);
+}
+
+// Replay of one frame in the reference's arithmetic (rare path of kArithChecked): samples straight from global
+// memory, exact channel, exact transform, exact decision stage.  Returns {packed rail errors, lane's sum |e|^2}.
+template <int NOISE>
+__device__ __noinline__ uint2 stream_frame_replay(const float2 *frame, const float *draws, const uint32_t *wb, double sigma_d,
+                                                  float2 *ws_tile, float2 *ws_lts)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 3, u = lane & 7;
+    Tw<true> tw; tw.load(u);
+    const ItemConst ic = make_items(lane);
+    const int n0 = grp == 0 ? 32 : grp == 1 ? 96 : grp == 2 ? 176 : 256;
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = n0 + u + 8 * slot_m<true>(i);
+        float2 smp = frame[n];
+        if (NOISE == kNoiseInject) smp.x = add_noise<true>(smp.x, draws[n], sigma_d, 0.f);
+        v[i] = smp;
+    }
+    fft64<true>(v, tw, ws_tile + grp * kGroupPitch, u);
+    float2 *dst = grp < 2 ? ws_lts + grp * kWin : ws_tile + (grp - 2) * kWin;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[u + 8 * j] = v[j];
+    __syncwarp();
+    float e2 = 0.f;
+    uint32_t pk = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const float2 A = ws_lts[ic.bin[t]], B = ws_lts[kWin + ic.bin[t]];
+        const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848
+        pk += item_eval<true>(ws_tile[ic.f_off[t]], Hh, ic.sc[t], wb[ic.word[t]] >> ic.shift[t], e2);
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&g_replayed_frames, 1ull);
+    return make_uint2(pk, __float_as_uint(e2));
+}
+
 // resident blocks per SM the launch bounds ask for: the fp32 kernels fit three (80 registers, <= 75 KB shared)
 static_assert(sizeof(StreamStage<false>) % 16 == 0 && sizeof(StreamStage<true>) % 16 == 0 && sizeof(StreamWarp<false>) % 16 == 0, "stage alignment");
-template <bool EXACT, int NOISE> constexpr int stream_blocks_per_sm() { return (!EXACT && NOISE != kNoiseInject) ? 3 : 2; }
+template <int ARITH, int NOISE> constexpr int stream_blocks_per_sm() { return (ARITH == kArithFast && NOISE != kNoiseInject) ? 3 : 2; }
 
-template <bool EXACT, int NOISE>
-__global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<EXACT, NOISE>()) k_stream_rx2(RxParams p)
+template <int ARITH, int NOISE>
+__global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()) k_stream_rx2(RxParams p)
 {
+    constexpr bool EXACT = ARITH == kArithExact;                // transform / decision arithmetic of the main path
+    constexpr bool CHECKED = ARITH == kArithChecked;
+    constexpr bool EXACT_CHANNEL = EXACT || CHECKED;
+    static_assert(!(CHECKED && NOISE == kNoisePhilox), "the replay reads the frame and the draws from global memory");
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
     __shared__ double s_sum[kWarpsPerBlock][2];
@@ -421,12 +528,14 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<EXACT, NOISE>()
             }
             tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
             float2 v[8];
+            float n2 = 0.f;                                       // CHECKED: the lane's share of the window's energy
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int m = slot_m<EXACT>(i);
                 float2 smp = ws.st[s].x[grp][u + 8 * m];
-                if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
-                if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
+                if (NOISE == kNoiseInject) smp.x = add_noise<EXACT_CHANNEL>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
+                if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT_CHANNEL>(smp.x, z[m], sigma_d, sigma_f);
+                if (CHECKED) n2 = fmaf(smp.x, smp.x, fmaf(smp.y, smp.y, n2));
                 v[i] = smp;
             }
             __syncwarp();                                         // every lane has its samples: the stage can be refilled
@@ -435,17 +544,42 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<EXACT, NOISE>()
             float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[u + 8 * j] = v[j];
+            if (CHECKED) {
+                const float r = window_radius(n2, p.radius_scale);
+                if (u == 0) ws.radius[grp] = r;
+            }
             __syncwarp();
             float f_e2 = 0.f;
             uint32_t pk = 0;
+            if (CHECKED) {
+                const float4 rad = *reinterpret_cast<const float4 *>(ws.radius);
+                const float rH = 0.5f * (rad.x + rad.y);
+                const float den_min = (kEvmGuard * rH) * (kEvmGuard * rH);
+                bool doubt = false;
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
-                const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848
-                const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
-                pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], w >> ic.shift[t], f_e2);
+                for (int t = 0; t < 3; ++t) {
+                    const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                    const float2 Hh = make_float2((A.x + B.x) * ic.sc[t], (A.y + B.y) * ic.sc[t]);
+                    const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
+                    const float rF = ic.f_off[t] < kWin ? rad.z : rad.w;          // which symbol the item belongs to
+                    pk += process_bin_checked(ws.tile[ic.f_off[t]], Hh, w >> ic.shift[t], rF, rH, den_min, f_e2, doubt);
+                }
+                __syncwarp();
+                if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
+                    const uint2 r = stream_frame_replay<NOISE>(p.in + f * len, NOISE == kNoiseInject ? p.g + f * len : nullptr,
+                                                               p.tx_bits + f * 6, sigma_d, ws.tile, &ws.lts[0][0]);
+                    pk = r.x; f_e2 = __uint_as_float(r.y);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                    const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848
+                    const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
+                    pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], w >> ic.shift[t], f_e2);
+                }
+                __syncwarp();
             }
-            __syncwarp();
             const bool any_err = __any_sync(0xffffffffu, pk != 0u);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) f_e2 += __shfl_xor_sync(0xffffffffu, f_e2, o);

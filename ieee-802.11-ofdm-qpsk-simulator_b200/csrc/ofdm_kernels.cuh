@@ -305,6 +305,7 @@ struct RxParams {
     long n_frames;
     int n_sym;
     float snr_lin;
+    float radius_scale;         // kArithChecked: error-radius factor (kRadius; infinity forces every frame to be replayed)
     uint32_t seed, stream;
     uint64_t frame0;
     ofdm_counters *counters;

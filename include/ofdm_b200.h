@@ -95,8 +95,15 @@ const char *ofdm_last_error(const ofdm_ctx *ctx);
 int ofdm_ctx_set_stream(ofdm_ctx *ctx, void *cuda_stream);   /* run on a caller-owned cudaStream_t */
 void *ofdm_ctx_stream(const ofdm_ctx *ctx);
 int ofdm_ctx_sync(ofdm_ctx *ctx);
-/* tuning / testing knobs: "force_generic_rx" = 1 routes every receiver call through the generic kernel */
+/* tuning / testing knobs:
+ *   "force_generic_rx"  = 1  routes every receiver call through the generic kernel
+ *   "exact_speculation" = 0  OFDM_MODE_EXACT sweeps run the reference's arithmetic on every frame instead of
+ *                            speculating in fp32, verifying, and replaying doubtful frames exactly (default 1;
+ *                            both give the same error counts)
+ *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path) */
 int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value);
+/* frames the speculating EXACT kernels replayed in the reference's arithmetic since start / the last reset (per process) */
+int ofdm_ctx_replayed_frames(ofdm_ctx *ctx, uint64_t *count, int reset);
 int ofdm_ctx_sm_count(const ofdm_ctx *ctx);
 uint64_t ofdm_ctx_launch_count(const ofdm_ctx *ctx);          /* kernels launched so far by this ctx */
 int ofdm_dev_alloc(ofdm_ctx *ctx, void **ptr, size_t bytes);

@@ -19,14 +19,28 @@ for l in sass:
         cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
     if m:
-        lines.append((cur, m.group(2).strip()))
+        lines.append((cur, m.group(2).strip(), int(m.group(1), 16)))
 rows = list(csv.reader(open(srccsv)))
 hdr = rows[1]; ia = hdr.index("Instructions Executed"); ist = hdr.index("Warp Stall Sampling (All Samples)")
-cnt = [(int(r[ia]), int(r[ist] or 0)) for r in rows[2:] if len(r) > ia and r[ia].isdigit()]
+body = [r for r in rows[2:] if len(r) > ia and r[ia].isdigit()]
+base = int(body[0][0], 16)
+cnt = {int(r[0], 16) - base: (int(r[ia]), int(r[ist] or 0), r[hdr.index("Source")]) for r in body}
 print("sass instrs:", len(lines), "ncu rows:", len(cnt))
 agg = collections.Counter(); st = collections.Counter()
-for (loc, txt), (n, s) in zip(lines, cnt):
-    agg[loc] += n; st[loc] += s
+# the profiled build may differ by a few instructions from the library on disk: align the two opcode streams
+import difflib
+def opc(t):
+    w = t.split()
+    return (w[1] if w[0].startswith("@") and len(w) > 1 else w[0])
+A = [opc(t) for _, t, _ in lines]
+B = [opc(r[hdr.index("Source")]) for r in body]
+sm = difflib.SequenceMatcher(None, A, B, autojunk=False)
+matched = 0
+for blk in sm.get_matching_blocks():
+    for i in range(blk.size):
+        loc = lines[blk.a + i][0]; r = body[blk.b + i]
+        agg[loc] += int(r[ia]); st[loc] += int(r[ist] or 0); matched += 1
+print("aligned instructions:", matched, "of", len(A), "/", len(B))
 srcs = {}
 tot = sum(agg.values())
 print("total per unit: %.1f" % (tot / units))
