@@ -220,12 +220,34 @@ def run_extras(o, pkg, torch, dev, args, rank, world):
     return out
 
 
+def bind_near_gpu(local):
+    """Pin this rank to the host cores next to its GPU (NVML's CPU affinity) before any pinned host memory is
+    allocated, so that the e2e path's H2D copies stay on the GPU's own NUMA node.  Returns a short description."""
+    if os.environ.get("OFDM_BENCH_AFFINITY", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use or use == allowed:
+            return "all %d cores are local" % len(allowed)
+        os.sched_setaffinity(0, use)
+        return "%d of %d cores" % (len(use), len(allowed))
+    except Exception as e:                      # affinity is an optimisation, never a requirement
+        return "unavailable (%s)" % type(e).__name__
+
+
 def run_gpu(args):
-    import torch
-    import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = bind_near_gpu(local)
+    import torch
+    import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -347,7 +369,8 @@ def run_gpu(args):
                 "config": {"workload": workload_name(n_frames), "frames_per_gpu": n_frames, "n_sym": N_SYM, "snr_db": [SNRS[0], SNRS[-1]],
                            "mode": "exact", "l2": "inputs larger than L2 (%.2f GB of draws + %.2f GB of TX IQ per sweep)"
                                                    % (g.numel() * 4 / 1e9, frames.numel() * 4 / 1e9),
-                           "parallelism": "frames sharded across %d GPU(s), one NCCL all-reduce of the counters" % world},
+                           "parallelism": "frames sharded across %d GPU(s), one NCCL all-reduce of the counters" % world,
+                           "host_affinity": affinity},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_total / args.steps,
                         # the draws of the guard interval / cyclic prefixes are never read by the receiver and stay on the host
                         "h2d_bytes_per_step": int(bits_h.numel() * 4 + n_frames * (128 + 64 * N_SYM) * 4),
