@@ -158,3 +158,27 @@ def test_sweep_entry_points_use_it(knobs, pkg):
     for x, y in zip(a, b):
         assert ints(x) == ints(y)
         assert abs(x.sum_err2 - y.sum_err2) <= 1e-5 * y.sum_err2
+
+
+def test_error_radius_has_margin(ofdm, pkg, port):
+    """The verification trusts |fp32 transform - reference transform| <= 512 u |x|_2 per bin.  Measured on
+    random, sparse, tonal and wide-dynamic-range inputs the distance stays far inside that radius."""
+    rng = np.random.default_rng(77)
+    n = 4000
+    x = rng.standard_normal((n, 64, 2)).astype(np.float32)
+    x[500:1000] *= np.exp(rng.uniform(-20, 20, (500, 1, 1))).astype(np.float32)                     # overall scale
+    x[1000:1500] *= np.exp(rng.uniform(-8, 8, (500, 64, 1))).astype(np.float32)                     # per-sample dynamic range
+    k = rng.integers(0, 64, 500); t = np.arange(64)
+    tone = np.exp(2j * np.pi * k[:, None] * t[None, :] / 64)                                        # single tones: one huge bin
+    x[1500:2000, :, 0] = tone.real; x[1500:2000, :, 1] = tone.imag
+    x[2000:2500] = 0; x[2000:2500, rng.integers(0, 64, 500), 0] = 1.0                               # impulses
+    x[2500:3000, :, 1] = 0                                                                          # real-only
+    x[3000:3500] = np.sign(x[3000:3500])                                                            # +-1 patterns
+    xd = ofdm.to_dev(x)
+    exact = ofdm.fft64(xd, pkg.MODE_EXACT).cpu().numpy().astype(np.float64)
+    fast = ofdm.fft64(xd, pkg.MODE_FAST).cpu().numpy().astype(np.float64)
+    assert np.array_equal(exact.astype(np.float32), port.fft64(x))                                  # exact = the reference's transform
+    err = np.sqrt(((exact - fast) ** 2).sum(axis=2)).max(axis=1)                                    # worst bin per window
+    norm = np.sqrt((x.astype(np.float64) ** 2).sum(axis=(1, 2)))
+    u = 2.0 ** -24
+    assert np.all(err <= 512 * u * norm / 20)                                                       # observed: a few u |x|_2
