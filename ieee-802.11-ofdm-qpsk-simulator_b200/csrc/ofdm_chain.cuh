@@ -312,7 +312,7 @@ __device__ __forceinline__ void wait(uint64_t *bar, uint32_t phase)
 }
 }  // namespace tma
 
-constexpr int kStages = 2;
+constexpr int kStages = 2;          // the ring indexing below (k & 1, k >> 1) relies on it
 
 template <bool WITH_DRAWS> struct alignas(16) StreamStage {     // bulk-copy destinations must be 16-byte aligned
     float2 x[4][kWin];              // LTS1, LTS2, sym0 body, sym1 body (skewed windows)
@@ -365,7 +365,7 @@ __device__ __forceinline__ float window_radius(float n2, float scale)
     n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
     n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(n2));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));          // flushing is harmless: n2 < 1e-30 is rejected
     return (n2 >= 1e-30f && n2 < 1e20f) ? scale * r : __int_as_float(0x7f800000);
 }
 
@@ -375,22 +375,27 @@ __device__ __forceinline__ float window_radius(float n2, float scale)
 // (|E|^2 ~ 1/|H|^2), where the fp32 transform's error in H would show: with |H| >= kEvmGuard radii the relative
 // error of an accepted quotient stays below ~2e-6 (the bound is about 300x the typical error).
 constexpr float kEvmGuard = 2048.f;
-__device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 Hh, uint32_t txp, float rF, float rH, float den_min, float &e2, bool &doubt)
+//
+// The estimate comes in unscaled, G = A + B with H = sc G, sc = +-0.5 (:848): powers of two commute with every rounding
+// here, so the test is done on G (numerator, thresholds and guards scaled accordingly, rH2 = 2 rH) and the quotient
+// is recovered with k = 4 sc = 1 / sc ... E = F conj(G) / |G|^2 * k; the sign of sc joins the sign comparison.
+__device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 G, float k, uint32_t txp, float rF, float rH2, float den_min4,
+                                                        float &e2, bool &doubt)
 {
-    const float a = F.x, b = F.y, c = Hh.x, d = Hh.y;
+    const float a = F.x, b = F.y, c = G.x, d = G.y;
     const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
     const float den = fmaf(c, c, d * d);
     float inv;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
-    const float ex = sr * inv, ey = si * inv;
     const uint32_t sq = txp << 31, sx = (txp ^ (txp >> 1)) << 31;          // IEEE sign bits of the tx Q / I rails
-    const uint32_t ei_ = (__float_as_uint(sr) ^ sx) >> 31, eq_ = (__float_as_uint(si) ^ sq) >> 31;
+    const uint32_t kb = __float_as_uint(k);
+    const uint32_t ei_ = (__float_as_uint(sr) ^ sx ^ kb) >> 31, eq_ = (__float_as_uint(si) ^ sq ^ kb) >> 31;
     const float fa = fabsf(a) + fabsf(b), hc = fabsf(c) + fabsf(d);
-    const float thr = fmaf(rF, hc + rH, fmaf(rH, fa, 1.2e-7f * (fa * hc)));
+    const float thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
     // reference numerator >= 1e-30 in magnitude and reference |H|^2 < 1e14: the float quotient keeps its sign (>= 1e-44)
-    const bool safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 1e-30f && den < 4e13f && den > den_min;
+    const bool safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 2e-30f && den < 1.6e14f && den > den_min4;
     doubt = doubt || !safe;
-    const float er = ex - __uint_as_float(0x3F3504F3u | sx), eim = ey - __uint_as_float(0x3F3504F3u | sq);
+    const float er = fmaf(sr * inv, k, -__uint_as_float(0x3F3504F3u | sx)), eim = fmaf(si * inv, k, -__uint_as_float(0x3F3504F3u | sq));
     e2 += fmaf(er, er, eim * eim);
     return ei_ | (eq_ << 8) | ((ei_ & eq_) << 16);
 }
@@ -454,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
     float2 *tile = ws.tile + grp * kGroupPitch;
     Tw<EXACT> tw; tw.load(u);
     const ItemConst ic = make_items(lane);
+    const float k4[3] = {4.f * ic.sc[0], 4.f * ic.sc[1], 4.f * ic.sc[2]};     // 1 / sc (CHECKED)
     constexpr int len = 320;
     const long stride = (long)gridDim.x * kWarpsPerBlock;
     const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp_u;
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
     uint32_t a_i = 0, a_q = 0, a_both = 0, a_ferr = 0, a_frames = 0;
     double a_e2 = 0.0, a_evm = 0.0;
     const int blk_base = (grp < 2 ? 8 + 16 * grp : 44 + 20 * (grp - 2)) + u;
-    long k = 0;
+    uint32_t k = 0;                                   // frames this warp has consumed (ring position)
     for (long f_chunk = f_first; f_chunk < p.n_frames; f_chunk += 32 * stride) {
         double sig_mine = 0.0;
         if (NOISE != kNoiseNone) {
@@ -510,8 +516,8 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
         for (int kk = 0; kk < 32; ++kk, ++k) {
             const long f = f_chunk + kk * stride;
             if (f >= p.n_frames) break;
-            const int s = (int)(k % kStages);
-            const uint32_t phase = (uint32_t)((k / kStages) & 1);
+            const int s = (int)(k & 1u);
+            const uint32_t phase = (k >> 1) & 1u;
             const double sigma_d = NOISE != kNoiseNone ? __shfl_sync(0xffffffffu, sig_mine, kk) : 0.0;
             const float sigma_f = (float)sigma_d;
             const double sigma_s = __dmul_rn(sigma_d, kTwScale);        // for add_noise_s
@@ -553,16 +559,17 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
             uint32_t pk = 0;
             if (CHECKED) {
                 const float4 rad = *reinterpret_cast<const float4 *>(ws.radius);
-                const float rH = 0.5f * (rad.x + rad.y);
-                const float den_min = (kEvmGuard * rH) * (kEvmGuard * rH);
+                const float rH2 = rad.x + rad.y;                                  // 2 r_H
+                const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
                 bool doubt = false;
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
-                    const float2 Hh = make_float2((A.x + B.x) * ic.sc[t], (A.y + B.y) * ic.sc[t]);
+                    const float2 G = make_float2(A.x + B.x, A.y + B.y);
                     const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
-                    const float rF = ic.f_off[t] < kWin ? rad.z : rad.w;          // which symbol the item belongs to
-                    pk += process_bin_checked(ws.tile[ic.f_off[t]], Hh, w >> ic.shift[t], rF, rH, den_min, f_e2, doubt);
+                    // items 0..31 belong to symbol 0, 64..95 to symbol 1, 32..63 split at lane 16
+                    const float rF = t == 0 ? rad.z : t == 2 ? rad.w : (lane < 16 ? rad.z : rad.w);
+                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], w >> ic.shift[t], rF, rH2, den_min4, f_e2, doubt);
                 }
                 __syncwarp();
                 if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
