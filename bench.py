@@ -217,6 +217,13 @@ def run_extras(o, pkg, torch, dev, args, rank, world):
         out["cfg3_mc_philox_" + name] = {"frames": nm, "snr_points": len(SNRS), "ms": ms,
                                          "symbols_per_s": nm * N_SYM * len(SNRS) / (ms * 1e-3),
                                          "fft_gflops": nm * len(SNRS) * 4 * 1920 / (ms * 1e-3) / 1e9}
+    # configs[4]: per-frame random multipath (8 taps drawn on chip) + LTS estimate + ZF equaliser, Philox noise;
+    # frames staged in HBM once per chunk (TX, fading, power), then one receiver pass per SNR point
+    mp = o.new_counters(len(SNRS))
+    for mode, name in ((pkg.MODE_FAST, "fast"), (pkg.MODE_EXACT, "exact")):
+        ms = timed(lambda: o.mc_sweep_multipath(11, rank * nm, nm, N_SYM, 8, SNRS, mode, counters=mp), reps=2)
+        out["cfg4_multipath_" + name] = {"frames": nm, "taps": 8, "snr_points": len(SNRS), "ms": ms,
+                                         "symbols_per_s": nm * N_SYM * len(SNRS) / (ms * 1e-3)}
     return out
 
 

@@ -187,11 +187,12 @@ int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
     if (!dump && p.n_sym == 2 && aligned && !ctx->force_generic) {
         if (mode == OFDM_MODE_EXACT) {
             // fp32 speculation + verification + exact replay: same counts as the all-exact kernel (ofdm_chain.cuh)
-            if (ctx->checked && noise != kNoisePhilox) {
+            if (ctx->checked) {
                 RxParams q = p;
                 q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
                 if (noise == kNoiseNone) return launch_stream<kArithChecked, kNoiseNone>(ctx, q);
-                return launch_stream<kArithChecked, kNoiseInject>(ctx, q);
+                if (noise == kNoiseInject) return launch_stream<kArithChecked, kNoiseInject>(ctx, q);
+                return launch_stream<kArithChecked, kNoisePhilox>(ctx, q);
             }
             if (noise == kNoiseNone) return launch_stream<kArithExact, kNoiseNone>(ctx, p);
             if (noise == kNoiseInject) return launch_stream<kArithExact, kNoiseInject>(ctx, p);

@@ -404,18 +404,28 @@ __device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 G, floa
 // memory, exact channel, exact transform, exact decision stage.  Returns {packed rail errors, lane's sum |e|^2}.
 template <int NOISE>
 __device__ __noinline__ uint2 stream_frame_replay(const float2 *frame, const float *draws, const uint32_t *wb, double sigma_d,
-                                                  float2 *ws_tile, float2 *ws_lts)
+                                                  uint32_t seed, uint32_t stream, uint64_t frame_id, float2 *ws_tile, float2 *ws_lts)
 {
     const int lane = threadIdx.x & 31, grp = lane >> 3, u = lane & 7;
     Tw<true> tw; tw.load(u);
     const ItemConst ic = make_items(lane);
     const int n0 = grp == 0 ? 32 : grp == 1 ? 96 : grp == 2 ? 176 : 256;
+    float z[8];
+    if (NOISE == kNoisePhilox) {                                  // the same draws as the speculated pass (window block layout)
+        const int blk_base = (grp < 2 ? 8 + 16 * grp : 44 + 20 * (grp - 2)) + u;
+        float za[4], zb[4];
+        philox_normals4(seed, stream, frame_id, (uint32_t)blk_base, kDomainNoise, za);
+        philox_normals4(seed, stream, frame_id, (uint32_t)(blk_base + 8), kDomainNoise, zb);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
+    }
     float2 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int n = n0 + u + 8 * slot_m<true>(i);
+        const int m = slot_m<true>(i), n = n0 + u + 8 * m;
         float2 smp = frame[n];
         if (NOISE == kNoiseInject) smp.x = add_noise<true>(smp.x, draws[n], sigma_d, 0.f);
+        if (NOISE == kNoisePhilox) smp.x = add_noise<true>(smp.x, z[m], sigma_d, 0.f);
         v[i] = smp;
     }
     fft64<true>(v, tw, ws_tile + grp * kGroupPitch, u);
@@ -446,7 +456,6 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
     constexpr bool EXACT = ARITH == kArithExact;                // transform / decision arithmetic of the main path
     constexpr bool CHECKED = ARITH == kArithChecked;
     constexpr bool EXACT_CHANNEL = EXACT || CHECKED;
-    static_assert(!(CHECKED && NOISE == kNoisePhilox), "the replay reads the frame and the draws from global memory");
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
     __shared__ double s_sum[kWarpsPerBlock][2];
@@ -574,7 +583,8 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
                 __syncwarp();
                 if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
                     const uint2 r = stream_frame_replay<NOISE>(p.in + f * len, NOISE == kNoiseInject ? p.g + f * len : nullptr,
-                                                               p.tx_bits + f * 6, sigma_d, ws.tile, &ws.lts[0][0]);
+                                                               p.tx_bits + f * 6, sigma_d, p.seed, p.stream, p.frame0 + (uint64_t)f,
+                                                               ws.tile, &ws.lts[0][0]);
                     pk = r.x; f_e2 = __uint_as_float(r.y);
                 }
             } else {

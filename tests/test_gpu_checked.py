@@ -182,3 +182,31 @@ def test_error_radius_has_margin(ofdm, pkg, port):
     norm = np.sqrt((x.astype(np.float64) ** 2).sum(axis=(1, 2)))
     u = 2.0 ** -24
     assert np.all(err <= 512 * u * norm / 20)                                                       # observed: a few u |x|_2
+
+
+@pytest.mark.parametrize("snr", [1.0, 7.0])
+def test_philox_noise_checked(knobs, pkg, snr):
+    """on-chip Philox draws: the replay regenerates the same draws; all routings give the same totals"""
+    ofdm = knobs
+    import torch
+    n, n_sym = 100_000, 2
+    gen = torch.Generator(device=ofdm.device); gen.manual_seed(5)
+    packed = torch.randint(-2**31, 2**31 - 1, (n * 6,), dtype=torch.int32, device=ofdm.device, generator=gen)
+    frames, power = ofdm.tx_frames(packed, n_sym, pkg.MODE_EXACT)
+    res = run_variants(ofdm, pkg, lambda: ofdm.awgn_rx_philox(frames, packed, snr, 77, 3, 1000, n_sym, pkg.MODE_EXACT, power=power)[0])
+    want = ints(res["all_exact"][0])
+    for name, (c, _) in res.items():
+        assert ints(c) == want, name
+    assert 0 < res["checked"][1] < n // 10 and res["replay_all"][1] == n
+
+
+def test_multipath_sweep_checked(knobs, pkg):
+    ofdm = knobs
+    snr = [2.0, 8.0, 14.0]
+    ofdm.set_option("exact_speculation", 1)
+    a = ofdm.mc_sweep_multipath(9, 0, 60_000, 2, 6, snr, pkg.MODE_EXACT)
+    ofdm.set_option("exact_speculation", 0)
+    b = ofdm.mc_sweep_multipath(9, 0, 60_000, 2, 6, snr, pkg.MODE_EXACT)
+    for x, y in zip(a, b):
+        assert ints(x) == ints(y)
+        assert abs(x.sum_err2 - y.sum_err2) <= 1e-5 * y.sum_err2
