@@ -118,6 +118,21 @@ def sample_inputs(n_frames, seed):
     return bits, g
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def cpu_baseline_single(sample_frames):
     """oracle/_ref (kind reference) or the port, one thread, bounded sample of the same workload."""
     po = entry.load_oracle()
@@ -131,7 +146,8 @@ def cpu_baseline_single(sample_frames):
         impl.chain(bits, g, N_SYM, s)
     dt = time.perf_counter() - t0
     return {"value": sample_frames * N_SYM * len(SNRS) / dt, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "%d frames x %d symbols x %d SNR points, injected normals, %.1f s" % (sample_frames, N_SYM, len(SNRS), dt)}
+            "sample": "%d frames x %d symbols x %d SNR points, injected normals, %.1f s" % (sample_frames, N_SYM, len(SNRS), dt),
+            "host": "%s, %d cores available" % (cpu_model(), host_cores())}
 
 
 def run_reference(args):
@@ -142,7 +158,7 @@ def run_reference(args):
     po = entry.load_oracle()
     po.build()
     kind = "reference" if po.have_ref() else "port"
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = host_cores()
     per_core = 192
     n_frames = per_core * cores
     bits, g = sample_inputs(n_frames, 4321)
@@ -162,7 +178,8 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": workload_name(args.frames), "reference_arm_sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "host": "%s, %d cores available" % (cpu_model(), cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
