@@ -225,6 +225,13 @@ def run_extras(o, pkg, torch, dev, args, rank, world):
         "symbols_per_s_tx_plus_rx": n * N_SYM / ((ms_tx + ms_rx) * 1e-3),
         "bytes_per_frame": {"tx": 24 + 2560, "rx": 2048 + 24},
         "note": "rx reads only the LTS halves and symbol bodies (2048 B of the 2560 B frame) + 24 B of bits"}
+    # the same in EXACT mode (bit-exact IQ from the transmitter; the receiver's totals through the checked arithmetic)
+    ms_txe = timed(lambda: o._check(lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), None, n, N_SYM, pkg.MODE_EXACT)))
+    ms_rxe = timed(lambda: o._check(lib.ofdm_rx_frames(h, frames.data_ptr(), bits.data_ptr(), n, N_SYM, pkg.MODE_EXACT, cnt.data_ptr(), None)))
+    out["cfg2_streaming_exact"] = {
+        "frames": n, "tx_ms": ms_txe, "tx_GBps": tx_bytes / ms_txe / 1e6, "tx_frac_of_hbm_peak": tx_bytes / ms_txe / 1e6 / peak,
+        "rx_ms": ms_rxe, "rx_GBps": rx_bytes / ms_rxe / 1e6, "rx_frac_of_hbm_peak": rx_bytes / ms_rxe / 1e6 / peak,
+        "symbols_per_s_tx_plus_rx": n * N_SYM / ((ms_txe + ms_rxe) * 1e-3)}
     del frames, bits
     torch.cuda.empty_cache()
     nm = args.mc_frames
@@ -234,6 +241,8 @@ def run_extras(o, pkg, torch, dev, args, rank, world):
         out["cfg3_mc_philox_" + name] = {"frames": nm, "snr_points": len(SNRS), "ms": ms,
                                          "symbols_per_s": nm * N_SYM * len(SNRS) / (ms * 1e-3),
                                          "fft_gflops": nm * len(SNRS) * 4 * 1920 / (ms * 1e-3) / 1e9}
+    out["next_rows_full_receiver_path"] = run_next_rows(o, pkg, torch, dev, peak)
+    torch.cuda.empty_cache()
     # configs[4]: per-frame random multipath (8 taps drawn on chip) + LTS estimate + ZF equaliser, Philox noise;
     # frames staged in HBM once per chunk (TX, fading, power), then one receiver pass per SNR point
     mp = o.new_counters(len(SNRS))
@@ -242,6 +251,62 @@ def run_extras(o, pkg, torch, dev, args, rank, world):
         out["cfg4_multipath_" + name] = {"frames": nm, "taps": 8, "snr_points": len(SNRS), "ms": ms,
                                          "symbols_per_s": nm * N_SYM * len(SNRS) / (ms * 1e-3)}
     return out
+
+
+def run_next_rows(o, pkg, torch, dev, peak, n=32768):
+    """SURVEY 8(f) rows, measured: the reference's whole over-the-air path, batched (STS || LTS || data, x2 RRC pulse shaping,
+    x10 repetition, AWGN over all 9800 samples, capture window, packet detection / selection, matched filter + decimation,
+    coarse + fine CFO, receiver).  Per stage: time (CUDA events) and algorithmic bytes (what the stage must read + write)."""
+    def timed(fn, reps=3):
+        out = fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record(); torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1) / reps
+
+    gen = torch.Generator(device=dev); gen.manual_seed(31)
+    packed = torch.randint(-2 ** 31, 2 ** 31 - 1, (n * N_SYM * 3,), dtype=torch.int32, device=dev, generator=gen)
+    starts = torch.randint(0, 9800 - 3008, (n,), dtype=torch.int32, device=dev, generator=gen)
+    stages = []
+
+    def stage(name, fn, nbytes):
+        out, ms = timed(fn)
+        stages.append({"stage": name, "ms": ms, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak})
+        return out
+
+    frames = stage("tx_frames (exact)", lambda: o.tx_frames(packed, N_SYM, pkg.MODE_EXACT, with_power=False), n * (24 + 2560))
+    full = stage("prepend_sts", lambda: o.prepend_sts(frames), n * (2560 + 3840))
+    shaped = stage("rrc_tx (x2 zero-stuff + 21-tap RRC)", lambda: o.rrc_tx(full), n * (3840 + 980 * 8))
+    rep = stage("gather (x10 repetition)", lambda: o.gather(shaped, 0, 9800), n * (980 * 8 + 9800 * 8))
+    ota = stage("awgn_philox_len (power + noise, 9800 samples)", lambda: o.awgn_philox_len(rep, 12.0, 5, 0, 0, pkg.MODE_FAST), n * (2 * 9800 * 8 + 9800 * 8))
+    del rep
+    cap = stage("gather (capture window, 3008 samples)", lambda: o.gather(ota, starts, 3008), n * 2 * 3008 * 8)
+    corr = stage("packet_detect", lambda: o.packet_detect(cap), n * (3008 * 8 + 2961 * 4))
+    idx = stage("packet_select", lambda: o.packet_select(corr), n * (2961 * 4 + 4))
+    fr = stage("rrc_rx_idx (matched filter + decimation)", lambda: o.rrc_rx_idx(cap, idx, 480), n * (3008 * 8 + 3840))
+    c1 = stage("cfo_coarse", lambda: o.cfo(fr, fine=False)[0], n * 2 * 3840)
+    c2 = stage("cfo_fine", lambda: o.cfo(c1, fine=True)[0], n * 2 * 3840)
+    lts_data = stage("gather (drop the STS)", lambda: o.gather(c2, 160, 320), n * (3840 + 2560))
+    stage("rx_frames (exact, totals)", lambda: o.rx_frames(lts_data, packed, N_SYM, pkg.MODE_EXACT)[0], n * (2048 + 24))
+    total_ms = sum(st["ms"] for st in stages)
+    res = {"frames": n, "stages": stages, "total_ms": total_ms, "frames_per_s": n / (total_ms * 1e-3),
+           "symbols_per_s": n * N_SYM / (total_ms * 1e-3)}
+    # the reference's own main() body for one SNR point (Transmitter + channel + Receiver), one host core
+    try:
+        po = entry.load_oracle(); po.build()
+        if po.have_ref():
+            r = po.Ref(); r.full_point(1, 2, 12.0)
+            t0 = time.perf_counter(); k = 0
+            while time.perf_counter() - t0 < 3.0:
+                r.full_point(10 + k, 20 + k, 12.0); k += 1
+            dt = time.perf_counter() - t0
+            res["cpu_reference_full_point"] = {"frames_per_s": k / dt, "cores": 1, "kind": "reference",
+                                               "sample": "%d single-frame points of the reference's main() body, %.1f s" % (k, dt)}
+    except Exception as exc:                   # the CPU figure is informational
+        res["cpu_reference_full_point"] = {"unavailable": type(exc).__name__}
+    return res
 
 
 def bind_near_gpu(local):
