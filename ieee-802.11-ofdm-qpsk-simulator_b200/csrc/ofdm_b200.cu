@@ -728,15 +728,18 @@ int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long
         p.seed = seed; p.frame0 = frame0; p.n_frames = n_frames; p.n_snr = n_snr; p.counters = counters;
         for (int i = 0; i < n_snr; ++i) { p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i])); }
         const size_t smem = mc_smem_bytes();
-        if (mode == OFDM_MODE_EXACT) {
-            OFDM_CUDA(ctx, cudaFuncSetAttribute(k_mc_philox<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int grid = grid_for(ctx, k_mc_philox<true>, smem, kWarpsPerBlock, n_frames);
-            k_mc_philox<true><<<grid, kThreads, smem, ctx->stream>>>(p);
-        } else {
-            OFDM_CUDA(ctx, cudaFuncSetAttribute(k_mc_philox<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int grid = grid_for(ctx, k_mc_philox<false>, smem, kWarpsPerBlock, n_frames);
-            k_mc_philox<false><<<grid, kThreads, smem, ctx->stream>>>(p);
-        }
+        p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+        auto launch = [&](auto k) -> int {
+            OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = grid_for(ctx, k, smem, kWarpsPerBlock, n_frames);
+            k<<<grid, kThreads, smem, ctx->stream>>>(p);
+            return OFDM_OK;
+        };
+        int st;
+        if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast>);
+        else if (ctx->checked) st = launch(k_mc_philox<kArithChecked>);
+        else st = launch(k_mc_philox<kArithExact>);
+        if (st) return st;
         return check_launch(ctx, "k_mc_philox");
     }
     // other frame shapes: the same streams through the staged kernels, in chunks that bound the scratch memory

@@ -50,6 +50,77 @@ __device__ __forceinline__ uint32_t item_eval(float2 F, float2 Hh, float sc, uin
     return process_bin_hot<EXACT>(F, Hh, sc, txp, true, e2);
 }
 
+// ---- arithmetic of the fused kernels (streaming receiver, Monte-Carlo) ----------------------------
+//   kArithFast     fp32 transform, fp32 channel, fp32 decisions
+//   kArithExact    the reference's arithmetic everywhere (ofdm_device.cuh, EXACT mode)
+//   kArithChecked  what OFDM_MODE_EXACT runs for the sweep: channel in the reference's arithmetic (so the
+//                  noisy time samples are the reference's bit for bit), transform and decisions speculated in
+//                  fp32, every decision verified against a rigorous bound on |fp32 path - reference path|,
+//                  and the whole frame replayed in the reference's arithmetic when any of its 192 rail
+//                  decisions is not provably the reference's.  Error counts are therefore exactly those of
+//                  kArithExact; the EVM sums differ by fp32 rounding (1e-5 contract), as they already do there.
+//
+// The bound.  Both transforms compute the same DFT of the same 64 floats x.  A radix-2 stage maps an error vector
+// with norm growth sqrt(2) and adds a local error of at most (eps_mul + u) |v_out|_2, u = 2^-24; |v_out|_2 after
+// stage s is 2^(s/2) |x|_2, so six stages give  |err|_2 <= 6 (eps_mul + u) 8 |x|_2.  Reference (OFDM.c:282-312:
+// double twiddle, product rounded to float, float add): eps_mul <= u(1 + 2^-26), i.e. <= 97 u |x|_2.  fp32 path
+// (dft8, float twiddles, FMA complex multiply, dft8): eps_mul <= 4u for a non-trivial factor, plus the separate
+// twiddle stage: <= (6*5 + 4) 8 u |x|_2 = 272 u |x|_2.  The channel estimate adds the rounding of A + B (:848):
+// <= 2u |A + B| <= 32 u max(|x_A|_2, |x_B|_2).  Every bin of a window is therefore within
+//      radius = kRadius * |x|_2,   kRadius = 512 u  (>= 97 + 272 + 32 = 401, the rest is margin for the
+// second-order terms, the approximate square root and the rounding of the threshold itself)
+// of the reference's value, for F, and (radius_A + radius_B)/2 for H.  With F = F~ + dF, H = H~ + dH the numerator
+// of the equaliser (:1050) moves by at most |dF| |H|_1 + |dH| |F|_1 + |dF||dH|, and its fp32 evaluation errs by
+// 2^-23 |F|_1 |H|_1 more (process_bin_hot).  The decision (:860-868) is the sign of the reference's numerator
+// whenever the quotient cannot underflow, which the magnitude guards below ensure.
+enum { kArithFast = 0, kArithExact = 1, kArithChecked = 2 };
+constexpr float kRadius = 512.f * 5.9604645e-8f;
+
+__device__ unsigned long long g_replayed_frames;     // frames the checked kernels replayed exactly (statistics)
+
+// radius of one window from the lane's share of sum |x|^2; windows whose energy is outside [1e-30, 1e20] are never
+// trusted (squares may have underflowed / the magnitude guards of the decision would not hold)
+__device__ __forceinline__ float window_radius(float n2, float scale)
+{
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));          // flushing is harmless: n2 < 1e-30 is rejected
+    return (n2 >= 1e-30f && n2 < 1e20f) ? scale * r : __int_as_float(0x7f800000);
+}
+
+// One data bin, speculated: like process_bin_hot<false>, and reports whether both rail decisions are provably the
+// reference's.  rF / rH: error radii of F and H.  den_min: bins whose |H|^2 is below it are not trusted either --
+// not for the decisions but for the EVM sum, which at low SNR is dominated by the few bins with a tiny estimate
+// (|E|^2 ~ 1/|H|^2), where the fp32 transform's error in H would show: with |H| >= kEvmGuard radii the relative
+// error of an accepted quotient stays below ~2e-6 (the bound is about 300x the typical error).
+constexpr float kEvmGuard = 2048.f;
+//
+// The estimate comes in unscaled, G = A + B with H = sc G, sc = +-0.5 (:848): powers of two commute with every rounding
+// here, so the test is done on G (numerator, thresholds and guards scaled accordingly, rH2 = 2 rH) and the quotient
+// is recovered with k = 4 sc = 1 / sc ... E = F conj(G) / |G|^2 * k; the sign of sc joins the sign comparison.
+__device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 G, float k, uint32_t txp, float rF, float rH2, float den_min4,
+                                                        float &e2, bool &doubt)
+{
+    const float a = F.x, b = F.y, c = G.x, d = G.y;
+    const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
+    const float den = fmaf(c, c, d * d);
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+    const uint32_t sq = txp << 31, sx = (txp ^ (txp >> 1)) << 31;          // IEEE sign bits of the tx Q / I rails
+    const uint32_t kb = __float_as_uint(k);
+    const uint32_t ei_ = (__float_as_uint(sr) ^ sx ^ kb) >> 31, eq_ = (__float_as_uint(si) ^ sq ^ kb) >> 31;
+    const float fa = fabsf(a) + fabsf(b), hc = fabsf(c) + fabsf(d);
+    const float thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
+    // reference numerator >= 1e-30 in magnitude and reference |H|^2 < 1e14: the float quotient keeps its sign (>= 1e-44)
+    const bool safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 2e-30f && den < 1.6e14f && den > den_min4;
+    doubt = doubt || !safe;
+    const float er = fmaf(sr * inv, k, -__uint_as_float(0x3F3504F3u | sx)), eim = fmaf(si * inv, k, -__uint_as_float(0x3F3504F3u | sq));
+    e2 += fmaf(er, er, eim * eim);
+    return ei_ | (eq_ << 8) | ((ei_ & eq_) << 16);
+}
+
 struct McParams {
     uint32_t seed;
     uint64_t frame0;
@@ -57,6 +128,7 @@ struct McParams {
     int n_snr;
     float snr_lin[kMaxSnr];         // (float)pow(10, snr/10), OFDM.c:645
     float inv_sqrt_snr[kMaxSnr];    // 1/sqrt(snr_lin), fast mode's noise scale factor
+    float radius_scale;             // kArithChecked: kRadius, or infinity to replay every point
     ofdm_counters *counters;        // [n_snr], accumulated into
 };
 
@@ -67,9 +139,53 @@ struct WarpShared {
     float2 body[2][kWin];           // the frame's two symbol bodies in time (skewed windows)
 };
 
-template <bool EXACT>
+// Replay of one (frame, SNR point) of the Monte-Carlo kernel in the reference's arithmetic (rare path of kArithChecked):
+// the same Philox draws, exact channel, exact transform, exact decision stage.  txp3: the lane's three bit pairs,
+// two bits each.  Returns {packed rail errors, lane's sum |e|^2}, not yet reduced over the warp.
+__device__ __noinline__ uint2 mc_point_replay(const float2 *src, double sigma_d, uint32_t seed, uint32_t stream, uint64_t fr,
+                                              uint32_t txp3, float2 *ws_tile, float2 *ws_lts)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 3, u = lane & 7;
+    Tw<true> tw; tw.load(u);
+    const ItemConst ic = make_items(lane);
+    const int blk_base = (grp < 2 ? 8 + 16 * grp : 44 + 20 * (grp - 2)) + u;
+    float za[4], zb[4];
+    philox_normals4(seed, stream, fr, (uint32_t)blk_base, kDomainNoise, za);
+    philox_normals4(seed, stream, fr, (uint32_t)(blk_base + 8), kDomainNoise, zb);
+    float2 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = slot_m<true>(i);
+        float2 s = src[u + 8 * m];
+        s.x = add_noise<true>(s.x, m < 4 ? za[m & 3] : zb[m & 3], sigma_d, 0.f);
+        r[i] = s;
+    }
+    fft64<true>(r, tw, ws_tile + grp * kGroupPitch, u);
+    float2 *dst = grp < 2 ? ws_lts + grp * kWin : ws_tile + (grp - 2) * kWin;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[u + 8 * j] = r[j];
+    __syncwarp();
+    float e2 = 0.f;
+    uint32_t pk = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const float2 A = ws_lts[ic.bin[t]], B = ws_lts[kWin + ic.bin[t]];
+        const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));
+        pk += item_eval<true>(ws_tile[ic.f_off[t]], Hh, ic.sc[t], (txp3 >> (2 * t)) & 3u, e2);
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&g_replayed_frames, 1ull);
+    return make_uint2(pk, __float_as_uint(e2));
+}
+
+// ARITH: kArithFast, kArithExact, or kArithChecked = exact transmitter, power and channel, receiver speculated in fp32
+// with verified decisions and exact replay (see above) -- the totals of kArithExact.
+template <int ARITH>
 __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
 {
+    constexpr bool EXACT = ARITH == kArithExact;                // receiver arithmetic of the main path
+    constexpr bool CHECKED = ARITH == kArithChecked;
+    constexpr bool TX_EXACT = EXACT || CHECKED;                 // transmitter, power, channel
     extern __shared__ __align__(128) unsigned char s_raw[];
     WarpShared *ws_all = reinterpret_cast<WarpShared *>(s_raw);
     float2 *s_ltsx = reinterpret_cast<float2 *>(s_raw + sizeof(WarpShared) * kWarpsPerBlock);   // [2][kWin] LTS halves, time
@@ -80,9 +196,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
     float2 *tile = ws.tile + grp * kGroupPitch;
     Tw<EXACT> tw; tw.load(u);
     const ItemConst ic = make_items(lane);
+    const float k4[3] = {4.f * ic.sc[0], 4.f * ic.sc[1], 4.f * ic.sc[2]};     // 1 / sc (CHECKED)
     int dmap_tx[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dmap_tx[i] = c_tab.bin_data[8 * slot_m<EXACT>(i) + u];
+    for (int i = 0; i < 8; ++i) dmap_tx[i] = c_tab.bin_data[8 * slot_m<TX_EXACT>(i) + u];
 
     for (int i = threadIdx.x; i < 128; i += kThreads) s_ltsx[(i >> 6) * kWin + (i & 63)] = c_tab.lts_time[32 + i];
     __syncthreads();
@@ -125,7 +242,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 else if (d == -3) x.x = -1.f;
                 v[i] = x;
             }
-            fft64<EXACT>(v, tw, tile, u);
+            if constexpr (CHECKED) {                              // the exact twiddles live only here: once per frame
+                Tw<true> twx; twx.load(u);
+                fft64<true>(v, twx, tile, u);
+            } else {
+                fft64<EXACT>(v, tw, tile, u);
+            }
             float pw = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -136,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 pw += (grp >= 2) ? (np >= 48 ? 2.f * e : e) : 0.f;      // the CP repeats samples 48..63
             }
             __syncwarp();
-            if (EXACT) {
+            if (TX_EXACT) {
                 // OFDM.c:637-643 on the 320-sample frame: the LTS prefix is a constant, the 160 data samples follow in order
                 double *terms = s_terms + warp * 160;
                 for (int i = lane; i < 160; i += 32) {
@@ -158,19 +280,31 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
         float sqrtP;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sqrtP) : "f"(P));
         // ---- SNR loop OFDM.c:1202: channel :635 + receiver :1018-1165 on the frame held in shared memory
+        // exact noise scale sqrt((double)(P / snr)) (:647, :651) of every SNR point, one (two) per lane, once per frame
+        double sig_lo = 0.0, sig_hi = 0.0;
+        if (TX_EXACT) {
+            if (lane < p.n_snr) sig_lo = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane]));
+            if (lane + 32 < p.n_snr) sig_hi = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane + 32]));
+        }
         for (int si = 0; si < p.n_snr; ++si) {
             double sigma_d = 0.0; float sigma_f;
-            if (EXACT) { sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si])); sigma_f = (float)sigma_d; sigma_d = __dmul_rn(sigma_d, kTwScale); }
-            else sigma_f = sqrtP * p.inv_sqrt_snr[si];
+            if (TX_EXACT) {
+                sigma_d = __shfl_sync(0xffffffffu, si < 32 ? sig_lo : sig_hi, si & 31);
+                sigma_f = (float)sigma_d;
+                if (EXACT) sigma_d = __dmul_rn(sigma_d, kTwScale);          // add_noise_s (the all-exact kernel is XU-bound)
+            } else sigma_f = sqrtP * p.inv_sqrt_snr[si];
             float za[4], zb[4];
             philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)blk_base, kDomainNoise, za);
             philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)(blk_base + 8), kDomainNoise, zb);
             float2 r[8];
+            float n2 = 0.f;                                       // CHECKED: the lane's share of the window's energy
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int m = slot_m<EXACT>(i);
                 float2 s = src[u + 8 * m];
-                s.x = add_noise_s<EXACT>(s.x, m < 4 ? za[m & 3] : zb[m & 3], sigma_d, sigma_f);
+                const float z = m < 4 ? za[m & 3] : zb[m & 3];
+                if (CHECKED) { s.x = add_noise<true>(s.x, z, sigma_d, sigma_f); n2 = fmaf(s.x, s.x, fmaf(s.y, s.y, n2)); }
+                else s.x = add_noise_s<EXACT>(s.x, z, sigma_d, sigma_f);
                 r[i] = s;
             }
             fft64<EXACT>(r, tw, tile, u);
@@ -178,16 +312,39 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
             float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[u + 8 * j] = r[j];
+            float rad = 0.f;
+            if (CHECKED) rad = window_radius(n2, p.radius_scale);
             __syncwarp();
             float e2 = 0.f;
             uint32_t pk = 0;
+            if (CHECKED) {
+                const float rA = __shfl_sync(0xffffffffu, rad, 0), rB = __shfl_sync(0xffffffffu, rad, 8);
+                const float r0 = __shfl_sync(0xffffffffu, rad, 16), r1 = __shfl_sync(0xffffffffu, rad, 24);
+                const float rH2 = rA + rB;                                        // 2 r_H
+                const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
+                bool doubt = false;
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
-                const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));
-                pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], txp[t], e2);
+                for (int t = 0; t < 3; ++t) {
+                    const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                    const float2 G = make_float2(A.x + B.x, A.y + B.y);
+                    const float rF = t == 0 ? r0 : t == 2 ? r1 : (lane < 16 ? r0 : r1);
+                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], txp[t], rF, rH2, den_min4, e2, doubt);
+                }
+                __syncwarp();
+                if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
+                    const uint32_t txp3 = (txp[0] & 3u) | ((txp[1] & 3u) << 2) | ((txp[2] & 3u) << 4);
+                    const uint2 rr = mc_point_replay(src, sigma_d, p.seed, (uint32_t)si, fr, txp3, ws.tile, &ws.lts[0][0]);
+                    pk = rr.x; e2 = __uint_as_float(rr.y);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                    const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));
+                    pk += item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], txp[t], e2);
+                }
+                __syncwarp();
             }
-            __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 pk += __shfl_xor_sync(0xffffffffu, pk, o);
@@ -329,77 +486,6 @@ template <bool WITH_DRAWS> struct alignas(16) StreamWarp {
     uint64_t bar[kStages];
     float radius[4];                // kArithChecked: error radius of each window's transform (see below)
 };
-// ---- arithmetic of the streaming receiver -------------------------------------------------------
-//   kArithFast     fp32 transform, fp32 channel, fp32 decisions
-//   kArithExact    the reference's arithmetic everywhere (ofdm_device.cuh, EXACT mode)
-//   kArithChecked  what OFDM_MODE_EXACT runs for the sweep: channel in the reference's arithmetic (so the
-//                  noisy time samples are the reference's bit for bit), transform and decisions speculated in
-//                  fp32, every decision verified against a rigorous bound on |fp32 path - reference path|,
-//                  and the whole frame replayed in the reference's arithmetic when any of its 192 rail
-//                  decisions is not provably the reference's.  Error counts are therefore exactly those of
-//                  kArithExact; the EVM sums differ by fp32 rounding (1e-5 contract), as they already do there.
-//
-// The bound.  Both transforms compute the same DFT of the same 64 floats x.  A radix-2 stage maps an error vector
-// with norm growth sqrt(2) and adds a local error of at most (eps_mul + u) |v_out|_2, u = 2^-24; |v_out|_2 after
-// stage s is 2^(s/2) |x|_2, so six stages give  |err|_2 <= 6 (eps_mul + u) 8 |x|_2.  Reference (OFDM.c:282-312:
-// double twiddle, product rounded to float, float add): eps_mul <= u(1 + 2^-26), i.e. <= 97 u |x|_2.  fp32 path
-// (dft8, float twiddles, FMA complex multiply, dft8): eps_mul <= 4u for a non-trivial factor, plus the separate
-// twiddle stage: <= (6*5 + 4) 8 u |x|_2 = 272 u |x|_2.  The channel estimate adds the rounding of A + B (:848):
-// <= 2u |A + B| <= 32 u max(|x_A|_2, |x_B|_2).  Every bin of a window is therefore within
-//      radius = kRadius * |x|_2,   kRadius = 512 u  (>= 97 + 272 + 32 = 401, the rest is margin for the
-// second-order terms, the approximate square root and the rounding of the threshold itself)
-// of the reference's value, for F, and (radius_A + radius_B)/2 for H.  With F = F~ + dF, H = H~ + dH the numerator
-// of the equaliser (:1050) moves by at most |dF| |H|_1 + |dH| |F|_1 + |dF||dH|, and its fp32 evaluation errs by
-// 2^-23 |F|_1 |H|_1 more (process_bin_hot).  The decision (:860-868) is the sign of the reference's numerator
-// whenever the quotient cannot underflow, which the magnitude guards below ensure.
-enum { kArithFast = 0, kArithExact = 1, kArithChecked = 2 };
-constexpr float kRadius = 512.f * 5.9604645e-8f;
-
-__device__ unsigned long long g_replayed_frames;     // frames the checked kernels replayed exactly (statistics)
-
-// radius of one window from the lane's share of sum |x|^2; windows whose energy is outside [1e-30, 1e20] are never
-// trusted (squares may have underflowed / the magnitude guards of the decision would not hold)
-__device__ __forceinline__ float window_radius(float n2, float scale)
-{
-    n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
-    n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
-    n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));          // flushing is harmless: n2 < 1e-30 is rejected
-    return (n2 >= 1e-30f && n2 < 1e20f) ? scale * r : __int_as_float(0x7f800000);
-}
-
-// One data bin, speculated: like process_bin_hot<false>, and reports whether both rail decisions are provably the
-// reference's.  rF / rH: error radii of F and H.  den_min: bins whose |H|^2 is below it are not trusted either --
-// not for the decisions but for the EVM sum, which at low SNR is dominated by the few bins with a tiny estimate
-// (|E|^2 ~ 1/|H|^2), where the fp32 transform's error in H would show: with |H| >= kEvmGuard radii the relative
-// error of an accepted quotient stays below ~2e-6 (the bound is about 300x the typical error).
-constexpr float kEvmGuard = 2048.f;
-//
-// The estimate comes in unscaled, G = A + B with H = sc G, sc = +-0.5 (:848): powers of two commute with every rounding
-// here, so the test is done on G (numerator, thresholds and guards scaled accordingly, rH2 = 2 rH) and the quotient
-// is recovered with k = 4 sc = 1 / sc ... E = F conj(G) / |G|^2 * k; the sign of sc joins the sign comparison.
-__device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 G, float k, uint32_t txp, float rF, float rH2, float den_min4,
-                                                        float &e2, bool &doubt)
-{
-    const float a = F.x, b = F.y, c = G.x, d = G.y;
-    const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
-    const float den = fmaf(c, c, d * d);
-    float inv;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
-    const uint32_t sq = txp << 31, sx = (txp ^ (txp >> 1)) << 31;          // IEEE sign bits of the tx Q / I rails
-    const uint32_t kb = __float_as_uint(k);
-    const uint32_t ei_ = (__float_as_uint(sr) ^ sx ^ kb) >> 31, eq_ = (__float_as_uint(si) ^ sq ^ kb) >> 31;
-    const float fa = fabsf(a) + fabsf(b), hc = fabsf(c) + fabsf(d);
-    const float thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
-    // reference numerator >= 1e-30 in magnitude and reference |H|^2 < 1e14: the float quotient keeps its sign (>= 1e-44)
-    const bool safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 2e-30f && den < 1.6e14f && den > den_min4;
-    doubt = doubt || !safe;
-    const float er = fmaf(sr * inv, k, -__uint_as_float(0x3F3504F3u | sx)), eim = fmaf(si * inv, k, -__uint_as_float(0x3F3504F3u | sq));
-    e2 += fmaf(er, er, eim * eim);
-    return ei_ | (eq_ << 8) | ((ei_ & eq_) << 16);
-}
-
 // Replay of one frame in the reference's arithmetic (rare path of kArithChecked): samples straight from global
 // memory, exact channel, exact transform, exact decision stage.  Returns {packed rail errors, lane's sum |e|^2}.
 template <int NOISE>

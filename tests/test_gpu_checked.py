@@ -210,3 +210,21 @@ def test_multipath_sweep_checked(knobs, pkg):
     for x, y in zip(a, b):
         assert ints(x) == ints(y)
         assert abs(x.sum_err2 - y.sum_err2) <= 1e-5 * y.sum_err2
+
+
+def test_monte_carlo_kernel_checked(knobs, pkg):
+    """fused on-chip Monte-Carlo in EXACT mode: speculation on / off / forced replay give identical totals"""
+    ofdm = knobs
+    snr = [float(s) for s in range(-2, 19, 2)]
+    n = 150_000
+    runs = {}
+    for name, spec, force in (("checked", 1, 0), ("all_exact", 0, 0), ("replay_all", 1, 1)):
+        ofdm.set_option("exact_speculation", spec); ofdm.set_option("force_replay", force)
+        ofdm.replayed_frames(reset=True)
+        runs[name] = (ofdm.mc_sweep_philox(2024, 5000, n, 2, snr, pkg.MODE_EXACT), ofdm.replayed_frames())
+    for x, y, z in zip(runs["checked"][0], runs["all_exact"][0], runs["replay_all"][0]):
+        assert ints(x) == ints(y) == ints(z)
+        assert abs(x.sum_err2 - y.sum_err2) <= 1e-5 * y.sum_err2
+        assert abs(z.sum_err2 - y.sum_err2) <= 1e-12 * y.sum_err2
+    assert runs["replay_all"][1] == n * len(snr) and runs["all_exact"][1] == 0
+    assert 0 < runs["checked"][1] < n * len(snr) // 10
