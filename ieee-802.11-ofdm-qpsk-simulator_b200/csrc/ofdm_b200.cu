@@ -899,8 +899,7 @@ int ofdm_packet_detect(ofdm_ctx *ctx, const float *rx, float *corr, long n, int 
     OFDM_REQUIRE(ctx, rx != nullptr && corr != nullptr);
     const size_t smem = (size_t)len * (sizeof(double) + sizeof(float2));
     OFDM_CUDA(ctx, cudaFuncSetAttribute(k_packet_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long full = (long)ctx->sm_count * 2;
-    int grid = (int)(n < full ? n : full);
+    int grid = grid_for(ctx, k_packet_detect, smem, 1, n);                  // one capture per block iteration, all resident blocks
     k_packet_detect<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(rx), corr, n, len);
     return check_launch(ctx, "k_packet_detect");
 }
@@ -910,7 +909,8 @@ int ofdm_packet_select(ofdm_ctx *ctx, const float *corr, int32_t *idx, long n, i
     OFDM_REQUIRE(ctx, n >= 0 && len_corr >= 1);
     if (n == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, corr != nullptr && idx != nullptr);
-    k_packet_select<<<blocks_1d(n), 256, 0, ctx->stream>>>(corr, idx, n, len_corr);
+    int grid = grid_for(ctx, k_packet_select, 0, kWarpsPerBlock, n);
+    k_packet_select<<<grid, kThreads, 0, ctx->stream>>>(corr, idx, n, len_corr);
     return check_launch(ctx, "k_packet_select");
 }
 

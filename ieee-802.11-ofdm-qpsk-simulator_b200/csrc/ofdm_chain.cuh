@@ -856,29 +856,35 @@ __global__ void __launch_bounds__(kThreads) k_rrc_rx(const float2 *__restrict__ 
 // Detection: delay 16, window 32, NO conjugate (as the reference and its MATLAB model).  Per lag i the reference
 // accumulates 32 float complex products sequentially and a float "peak" fed with double cabs()^2 terms, then
 // out_i = (float)(cabs(corr)^2 / (double)(float)(peak*peak)); the sequential float sums differ per lag, so there is
-// no sliding-window reuse if the bits are to match.  One block per capture: samples and their |.|^2 terms (glibc
-// hypot, once per sample) staged in shared memory, one lag per thread.
+// no sliding-window reuse of the sums if the bits are to match.  What the lags do share is the summands: the float
+// product rx[n] * rx[n+16] (separately rounded multiplies, :674) and the double term cabs(rx[n])^2 (glibc hypot, :675) are
+// computed once per sample and staged in shared memory; each thread then runs its lag's two 32-term chains over them.
 __global__ void __launch_bounds__(kThreads) k_packet_detect(const float2 *__restrict__ rx, float *__restrict__ corr, long n, int len)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     double *pk2 = reinterpret_cast<double *>(s_raw);
-    float2 *sx = reinterpret_cast<float2 *>(pk2 + len);
+    float2 *prod = reinterpret_cast<float2 *>(pk2 + len);
     const int n_corr = len - 47;
     for (long c = blockIdx.x; c < n; c += gridDim.x) {
+        const float2 *x = rx + c * len;
         for (int i = threadIdx.x; i < len; i += kThreads) {
-            const float2 v = rx[c * len + i];
-            sx[i] = v;
-            const double h = hypot_glibc((double)v.x, (double)v.y);          // cabs :675
+            const float2 a = x[i];
+            const double h = hypot_glibc((double)a.x, (double)a.y);          // cabs :675
             pk2[i] = __dmul_rn(h, h);
+            if (i + 16 < len) {
+                const float2 b = x[i + 16];
+                prod[i] = make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),      // :674, float complex multiply
+                                      __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+            }
         }
         __syncthreads();
         for (int i = threadIdx.x; i < n_corr; i += kThreads) {
             float cr = 0.f, ci = 0.f, peak = 0.f;
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < 32; ++k) {
-                const float2 a = sx[i + k], b = sx[i + k + 16];
-                cr = __fadd_rn(cr, __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)));      // :674
-                ci = __fadd_rn(ci, __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+                const float2 t = prod[i + k];
+                cr = __fadd_rn(cr, t.x);
+                ci = __fadd_rn(ci, t.y);
                 peak = __double2float_rn(__dadd_rn((double)peak, pk2[i + k + 16]));           // :675
             }
             const double hc = hypot_glibc((double)cr, (double)ci);
@@ -891,26 +897,32 @@ __global__ void __launch_bounds__(kThreads) k_packet_detect(const float2 *__rest
 // Selection OFDM.c:685-771: indices above 0.75; a gap > 300 to the previous one opens a candidate; all candidates but
 // the last are tried in order and the first whose correlation 230 lags later is still above the threshold wins:
 // packet_idx = candidate + len_RRC_rx + 1 (= +11); 0 if none.  One thread per capture (the scan is sequential).
-__global__ void k_packet_select(const float *__restrict__ corr, int32_t *__restrict__ idx_out, long n, int len_corr)
+__global__ void __launch_bounds__(kThreads) k_packet_select(const float *__restrict__ corr, int32_t *__restrict__ idx_out, long n, int len_corr)
 {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const float *x = corr + c * len_corr;
-    int n_fronts = 0, prev = -1;
-    for (int i = 0; i < len_corr; ++i)
-        if (fabsf(x[i]) > 0.75f) { if (i - prev > 300) ++n_fronts; prev = i; }
-    int result = 0, fronts = 0;
-    prev = -1;
-    for (int i = 0; i < len_corr && result == 0; ++i) {
-        if (!(fabsf(x[i]) > 0.75f)) continue;
-        const bool front = i - prev > 300;
-        prev = i;
-        if (!front) continue;
-        if (++fronts > n_fronts - 1) break;                                  // x < packet_front_count - 1  (:754)
-        const int look = i + 230;                                            // :756 (unchecked in the reference)
-        if (look < len_corr && fabsf(x[look]) > 0.75f) result = i + 11;      // :758
+    // One warp per capture, 32 lags per step (coalesced); everything below the ballot is warp-uniform.  Within a step only
+    // the first lag above the threshold can open a candidate (the others follow within 32 < 300 lags).  A candidate is tried
+    // when the next one appears, so the last one never is -- "x < packet_front_count - 1" (:754).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long c = (long)blockIdx.x * kWarpsPerBlock + warp; c < n; c += (long)gridDim.x * kWarpsPerBlock) {
+        const float *x = corr + c * len_corr;
+        int prev = -1, pending = -1, result = 0;
+        for (int base = 0; base < len_corr && result == 0; base += 32) {
+            const int i = base + lane;
+            const bool above = i < len_corr && fabsf(x[i]) > 0.75f;
+            const uint32_t mask = __ballot_sync(0xffffffffu, above);
+            if (mask == 0u) continue;
+            const int first = base + __ffs((int)mask) - 1;
+            if (first - prev > 300) {                                            // a new candidate: the pending one is not the last
+                if (pending >= 0) {
+                    const int look = pending + 230;                              // :756 (unchecked in the reference)
+                    if (look < len_corr && fabsf(x[look]) > 0.75f) result = pending + 11;     // :758
+                }
+                pending = first;
+            }
+            prev = base + 31 - __clz((int)mask);
+        }
+        if (lane == 0) idx_out[c] = result;
     }
-    idx_out[c] = result;
 }
 
 // ------------------------------------------------------------------------------------------------
