@@ -17,6 +17,7 @@ namespace ofdm {
 
 constexpr int kWin = 72;            // skewed pitch of a 64-sample window in shared memory (bank-conflict-free groups)
 constexpr int kMaxSnr = 64;
+constexpr int kMaxTaps = 16;
 
 struct ItemConst {
     int f_off[3];                   // where the item's FFT output sits in the F exchange tile: sym*kWin + bin
@@ -94,8 +95,9 @@ __device__ __forceinline__ float window_radius(float n2, float scale)
 // reference's.  rF / rH: error radii of F and H.  den_min: bins whose |H|^2 is below it are not trusted either --
 // not for the decisions but for the EVM sum, which at low SNR is dominated by the few bins with a tiny estimate
 // (|E|^2 ~ 1/|H|^2), where the fp32 transform's error in H would show: with |H| >= kEvmGuard radii the relative
-// error of an accepted quotient stays below ~2e-6 (the bound is about 300x the typical error).
-constexpr float kEvmGuard = 2048.f;
+// error of an accepted quotient stays below ~1e-5 for the rarest accepted bins (the bound is about 300x the typical
+// error) and the sums agree with the all-exact kernel's to ~1e-7 (2048 radii: 1e-8, at 4x the replays on fading channels).
+constexpr float kEvmGuard = 512.f;
 //
 // The estimate comes in unscaled, G = A + B with H = sc G, sc = +-0.5 (:848): powers of two commute with every rounding
 // here, so the test is done on G (numerator, thresholds and guards scaled accordingly, rH2 = 2 rH) and the quotient
@@ -129,6 +131,7 @@ struct McParams {
     float snr_lin[kMaxSnr];         // (float)pow(10, snr/10), OFDM.c:645
     float inv_sqrt_snr[kMaxSnr];    // 1/sqrt(snr_lin), fast mode's noise scale factor
     float radius_scale;             // kArithChecked: kRadius, or infinity to replay every point
+    int n_taps;                     // multipath variant: taps per frame (1..kMaxTaps)
     ofdm_counters *counters;        // [n_snr], accumulated into
 };
 
@@ -180,7 +183,17 @@ __device__ __noinline__ uint2 mc_point_replay(const float2 *src, double sigma_d,
 
 // ARITH: kArithFast, kArithExact, or kArithChecked = exact transmitter, power and channel, receiver speculated in fp32
 // with verified decisions and exact replay (see above) -- the totals of kArithExact.
-template <int ARITH>
+// MP = true is configs[4] fused the same way: per-frame random taps (Philox domain 2, as k_multipath<true>) are applied
+// to the whole 320-sample frame in shared memory (same operation order as k_multipath), the power is that of the faded
+// frame (as frame_power() computes it), and the SNR loop runs on the faded windows.
+struct MpWarp {
+    float2 fx[320];                 // the transmitted frame, LTS || (CP + body) x 2
+    float2 fw[4][kWin];             // faded LTS halves and symbol bodies (skewed windows)
+    float2 sh[kMaxTaps];            // this frame's taps
+};
+template <bool MP> __host__ __device__ constexpr int mc_terms_per_warp() { return MP ? 320 : 160; }
+
+template <int ARITH, bool MP = false>
 __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
 {
     constexpr bool EXACT = ARITH == kArithExact;                // receiver arithmetic of the main path
@@ -189,7 +202,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
     extern __shared__ __align__(128) unsigned char s_raw[];
     WarpShared *ws_all = reinterpret_cast<WarpShared *>(s_raw);
     float2 *s_ltsx = reinterpret_cast<float2 *>(s_raw + sizeof(WarpShared) * kWarpsPerBlock);   // [2][kWin] LTS halves, time
-    double *s_terms = reinterpret_cast<double *>(s_ltsx + 2 * kWin);                            // [warps][160] (EXACT power)
+    double *s_terms = reinterpret_cast<double *>(s_ltsx + 2 * kWin);                            // [warps][160 | 320] (EXACT power)
+    MpWarp *mp_all = reinterpret_cast<MpWarp *>(s_terms + kWarpsPerBlock * mc_terms_per_warp<MP>());
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
     WarpShared &ws = ws_all[warp];
@@ -202,9 +216,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
     for (int i = 0; i < 8; ++i) dmap_tx[i] = c_tab.bin_data[8 * slot_m<TX_EXACT>(i) + u];
 
     for (int i = threadIdx.x; i < 128; i += kThreads) s_ltsx[(i >> 6) * kWin + (i & 63)] = c_tab.lts_time[32 + i];
+    if (MP) {                                                    // the LTS slot of the frame never changes
+        MpWarp &mw = mp_all[warp];
+        for (int i = lane; i < 160; i += 32) mw.fx[i] = c_tab.lts_time[i];
+    }
     __syncthreads();
 
-    const float2 *src = grp < 2 ? s_ltsx + grp * kWin : ws.body[grp - 2];
+    const float2 *src = MP ? mp_all[warp].fw[grp] : (grp < 2 ? s_ltsx + grp * kWin : ws.body[grp - 2]);
     const int blk_base = (grp < 2 ? 8 + 16 * grp : 44 + 20 * (grp - 2)) + u;        // window_block_base(n0) + u
     const double q = (double)kQpsk;
     const float inv_ref2 = (float)(1.0 / (96.0 * (2.0 * q * q)));
@@ -253,12 +271,55 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
             for (int j = 0; j < 8; ++j) {
                 const int np = u + 8 * ((j + 4) & 7);
                 const float2 y = make_float2(v[j].x * 0.015625f, -v[j].y * 0.015625f);
-                if (grp >= 2) ws.body[grp - 2][np] = y;
-                const float e = fmaf(y.x, y.x, y.y * y.y);
-                pw += (grp >= 2) ? (np >= 48 ? 2.f * e : e) : 0.f;      // the CP repeats samples 48..63
+                if (MP) {
+                    if (grp >= 2) {
+                        float2 *sym = mp_all[warp].fx + 160 + 80 * (grp - 2);
+                        sym[16 + np] = y;
+                        if (np >= 48) sym[np - 48] = y;                 // cyclic prefix :559-565
+                    }
+                } else {
+                    if (grp >= 2) ws.body[grp - 2][np] = y;
+                    const float e = fmaf(y.x, y.x, y.y * y.y);
+                    pw += (grp >= 2) ? (np >= 48 ? 2.f * e : e) : 0.f;  // the CP repeats samples 48..63
+                }
             }
             __syncwarp();
-            if (TX_EXACT) {
+            if (MP) {
+                MpWarp &mw = mp_all[warp];
+                const int n_taps = p.n_taps;
+                if (2 * lane < n_taps) {                                // taps of this frame: k_multipath<true>
+                    const float scale = sqrtf(0.5f / (float)n_taps);
+                    float z[4];
+                    philox_normals4(p.seed, 0u, fr, (uint32_t)lane, kDomainTaps, z);
+                    mw.sh[2 * lane] = make_float2(scale * z[0], scale * z[1]);
+                    if (2 * lane + 1 < n_taps) mw.sh[2 * lane + 1] = make_float2(scale * z[2], scale * z[3]);
+                }
+                __syncwarp();
+                double *terms = s_terms + warp * 320;
+                for (int n = lane; n < 320; n += 32) {                   // y[n] = sum_l h[l] x[n-l], descending l, no FMA
+                    float ar = 0.f, ai = 0.f;
+                    for (int l = (n_taps - 1 < n ? n_taps - 1 : n); l >= 0; --l) {
+                        const float2 a = mw.fx[n - l], b = mw.sh[l];
+                        ar = __fadd_rn(ar, __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)));
+                        ai = __fadd_rn(ai, __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+                    }
+                    // the windows the receiver reads: 32..95, 96..159, 176..239, 256..319
+                    const int w = n < 160 ? (n >= 32 ? (n - 32) >> 6 : -1) : ((n - 160) % 80 >= 16 ? 2 + (n - 160) / 80 : -1);
+                    if (w >= 0) mw.fw[w][w < 2 ? (n - 32) & 63 : (n - 160) % 80 - 16] = make_float2(ar, ai);
+                    if (TX_EXACT) { const double h = hypot_glibc((double)ar, (double)ai); terms[n] = __dmul_rn(h, h); }
+                    else pw = fmaf(ar, ar, fmaf(ai, ai, pw));            // k_frame_power_fast's order
+                }
+                __syncwarp();
+                if (TX_EXACT) {                                          // frame_power(): the whole faded frame, in order
+                    float acc = 0.f;
+                    if (lane == 0) for (int i = 0; i < 320; ++i) acc = __double2float_rn(__dadd_rn((double)acc, terms[i]));
+                    P = __fdiv_rn(__shfl_sync(0xffffffffu, acc, 0), 320.f);
+                } else {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+                    P = pw / 320.f;
+                }
+            } else if (TX_EXACT) {
                 // OFDM.c:637-643 on the 320-sample frame: the LTS prefix is a constant, the 160 data samples follow in order
                 double *terms = s_terms + warp * 160;
                 for (int i = lane; i < 160; i += 32) {
@@ -387,9 +448,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
     }
 }
 
-inline size_t mc_smem_bytes()
+inline size_t mc_smem_bytes(bool multipath = false)
 {
-    return sizeof(WarpShared) * kWarpsPerBlock + 2 * kWin * sizeof(float2) + kWarpsPerBlock * 160 * sizeof(double);
+    return sizeof(WarpShared) * kWarpsPerBlock + 2 * kWin * sizeof(float2) + kWarpsPerBlock * (multipath ? 320 : 160) * sizeof(double) +
+           (multipath ? sizeof(MpWarp) * kWarpsPerBlock : 0);
 }
 
 // payload bits of the Philox bit stream, for callers that want the same frames in HBM (symbol s = block s)
@@ -735,7 +797,6 @@ namespace ofdm {
 // ([frames][n_taps] complex) or drawn on chip: i.i.d. complex Gaussian, E|h_l|^2 = 1/n_taps, Philox domain 2,
 // tap l = normals (2l, 2l+1) of block l/2.  Same float operation order as the oracle (orc_apply_taps):
 // descending l, separate multiplies and adds (no FMA), so supplied taps reproduce it bit for bit.
-constexpr int kMaxTaps = 16;
 
 template <bool PHILOX>
 __global__ void __launch_bounds__(kThreads) k_multipath(const float2 *__restrict__ tx, const float2 *__restrict__ taps, uint32_t seed,

@@ -100,7 +100,10 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *   "exact_speculation" = 0  OFDM_MODE_EXACT sweeps run the reference's arithmetic on every frame instead of
  *                            speculating in fp32, verifying, and replaying doubtful frames exactly (default 1;
  *                            both give the same error counts)
- *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path) */
+ *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path)
+ *   "multipath_path"    = 0  ofdm_mc_sweep_multipath_dev picks the faster of its two implementations per mode (default);
+ *                       = 1  frames staged in HBM (TX, fading, power, one receiver kernel per SNR point);
+ *                       = 2  the fused on-chip kernel; both give the same totals */
 int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value);
 /* frames the speculating EXACT kernels replayed in the reference's arithmetic since start / the last reset (per process) */
 int ofdm_ctx_replayed_frames(ofdm_ctx *ctx, uint64_t *count, int reset);

@@ -78,3 +78,29 @@ def test_c_driver_multipath_sweep(tmp_path):
     evm = [float(w) for w in open(out / "Output_EVM_AGC.txt").read().split()]
     assert len(ber) == 8 and all(a >= b for a, b in zip(ber, ber[1:])) and ber[0] > 0.05 and 0 < ber[-1] < ber[0] / 10
     assert all(np.isfinite(e) for e in evm)
+
+
+@pytest.mark.parametrize("n_taps", [1, 5, 8, 16])
+def test_fused_multipath_sweep_equals_staged(ofdm, pkg, n_taps):
+    """configs[4] on chip (k_mc_philox<., multipath>) against the staged path (TX, k_multipath, frame power, per-SNR receiver
+    kernels over HBM): the same taps, draws and arithmetic -> identical integer totals in both modes, EVM sums to rounding"""
+    snr = [0.0, 6.0, 12.0, 18.0]
+    n = 40_000
+    try:
+        for mode in (pkg.MODE_EXACT, pkg.MODE_FAST):
+            ofdm.set_option("multipath_path", 2)
+            fused = ofdm.mc_sweep_multipath(21, 700, n, 2, n_taps, snr, mode)
+            ofdm.set_option("multipath_path", 1)
+            staged = ofdm.mc_sweep_multipath(21, 700, n, 2, n_taps, snr, mode)
+            ofdm.set_option("force_generic_rx", 1)                      # ... and through the generic receiver kernel
+            generic = ofdm.mc_sweep_multipath(21, 700, n, 2, n_taps, snr, mode)
+            ofdm.set_option("force_generic_rx", 0)
+            for a, b in zip(generic, staged):
+                assert (a.bit_errors, a.frames_in_error, a.rail_errors) == (b.bit_errors, b.frames_in_error, b.rail_errors), (n_taps, mode)
+            for a, b in zip(fused, staged):
+                assert (a.bit_errors, a.bits, a.frames_in_error, a.rail_errors, a.frames) == \
+                       (b.bit_errors, b.bits, b.frames_in_error, b.rail_errors, b.frames), (n_taps, mode)
+                assert abs(a.sum_err2 - b.sum_err2) <= 1e-5 * b.sum_err2
+    finally:
+        ofdm.set_option("force_generic_rx", 0)
+        ofdm.set_option("multipath_path", 0)
