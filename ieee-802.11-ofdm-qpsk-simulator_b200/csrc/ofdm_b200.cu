@@ -21,6 +21,7 @@ struct ofdm_ctx {
     bool force_generic = false;      // testing knob: route n_sym == 2 sweeps through the generic kernel too
     bool checked = true;             // EXACT sweeps speculate in fp32, verify, and replay exactly (kArithChecked)
     bool force_replay = false;       // testing knob: the verification fails every frame
+    bool general_stream = false;     // testing knob: two-symbol frames through the multi-pass streaming kernel too
     int multipath_path = 0;          // configs[4]: 0 = auto (fast: fused on-chip kernel, exact: HBM-staged frames), 1 = staged, 2 = fused
     char err[256] = {0};
     float lts_freq[128];
@@ -179,12 +180,38 @@ int launch_stream(ofdm_ctx *ctx, const RxParams &p)
     return check_launch(ctx, "k_stream_rx2");
 }
 
+template <int ARITH, int NOISE>
+int launch_stream_n(ofdm_ctx *ctx, const RxParams &p)
+{
+    auto k = k_stream_rxn<ARITH, NOISE>;
+    const size_t smem = stream_smem_bytes<NOISE>();
+    OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
+    k<<<grid, kThreads, smem, ctx->stream>>>(p);
+    return check_launch(ctx, "k_stream_rxn");
+}
+template <int NOISE>
+int launch_stream_n_mode(ofdm_ctx *ctx, int mode, const RxParams &p)
+{
+    if (mode != OFDM_MODE_EXACT) return launch_stream_n<kArithFast, NOISE>(ctx, p);
+    if (!ctx->checked) return launch_stream_n<kArithExact, NOISE>(ctx, p);
+    RxParams q = p;
+    q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+    return launch_stream_n<kArithChecked, NOISE>(ctx, q);
+}
+
 int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
 {
     const ofdm_rx_dump &d = p.dump;
     const bool dump = d.H || d.eq || d.sliced || d.bits || d.frame_bit_errors || d.frame_evm_lin;
     // default frame shape without per-bin outputs: the TMA-staged streaming kernel (bulk copies need 16-byte alignment)
     const bool aligned = ((uintptr_t)p.in % 16 == 0) && (noise != kNoiseInject || (uintptr_t)p.g % 16 == 0);
+    // other frame shapes (or "general_stream" = 1): the multi-pass streaming kernel
+    if (!dump && aligned && !ctx->force_generic && (p.n_sym != 2 || ctx->general_stream)) {
+        if (noise == kNoiseNone) return launch_stream_n_mode<kNoiseNone>(ctx, mode, p);
+        if (noise == kNoiseInject) return launch_stream_n_mode<kNoiseInject>(ctx, mode, p);
+        return launch_stream_n_mode<kNoisePhilox>(ctx, mode, p);
+    }
     if (!dump && p.n_sym == 2 && aligned && !ctx->force_generic) {
         if (mode == OFDM_MODE_EXACT) {
             // fp32 speculation + verification + exact replay: same counts as the all-exact kernel (ofdm_chain.cuh)
@@ -357,6 +384,7 @@ int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "force_generic_rx")) { ctx->force_generic = value != 0; return OFDM_OK; }
     if (!strcmp(name, "exact_speculation")) { ctx->checked = value != 0; return OFDM_OK; }
     if (!strcmp(name, "force_replay")) { ctx->force_replay = value != 0; return OFDM_OK; }
+    if (!strcmp(name, "general_stream")) { ctx->general_stream = value != 0; return OFDM_OK; }
     if (!strcmp(name, "multipath_path")) { if (value < 0 || value > 2) return fail(ctx, OFDM_ERR_INVALID, "multipath_path: 0..2"); ctx->multipath_path = value; return OFDM_OK; }
     return fail(ctx, OFDM_ERR_INVALID, "unknown option");
 }

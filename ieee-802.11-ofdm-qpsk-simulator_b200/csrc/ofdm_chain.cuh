@@ -785,6 +785,344 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The streaming receiver for any number of data symbols.  A frame is a sequence of passes through the same ring:
+// pass 0 = {LTS half 1, LTS half 2, symbol 0, symbol 1} exactly as k_stream_rx2, then four symbols per pass against the
+// channel estimate left in shared memory by pass 0, their 192 data bins dealt out six per lane.  kArithChecked marks a frame whose
+// decisions are not all provably the reference's and replays it whole (sweep_frame_replay) after its last pass.
+struct SweepLane {                  // per-lane constants for the natural bins u + 8j
+    uint32_t dlo, dhi;              // data index bytes (>= 0x80: null / pilot), j = 0..3 and 4..7
+    uint32_t lneg, lnul;            // bit j: L < 0, L == 0
+};
+__device__ __forceinline__ SweepLane make_sweep_lane(int u)
+{
+    SweepLane c = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t d = (uint32_t)(uint8_t)c_tab.bin_data[u + 8 * j];
+        if (j < 4) c.dlo |= d << (8 * j); else c.dhi |= d << (8 * (j - 4));
+        const int l = c_tab.bin_lts[u + 8 * j];
+        c.lneg |= (uint32_t)(l < 0) << j; c.lnul |= (uint32_t)(l == 0) << j;
+    }
+    return c;
+}
+struct SweepFrame {                 // one frame's inputs
+    const float2 *x; const float *g; const uint32_t *bits;
+    int n_sym; double sigma_d; uint32_t seed, stream; uint64_t frame_id;
+};
+struct SweepTotals { uint32_t i, q, both; float e2; };
+
+// One frame in the reference's arithmetic, samples straight from global memory (the replay of k_stream_rxn<kArithChecked>).
+template <int NOISE>
+__device__ __noinline__ SweepTotals sweep_frame_replay(SweepFrame fr, float2 *tile_w, float2 *lts /* [2][kWin] */)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 3, u = lane & 7;
+    float2 *tile = tile_w + grp * kGroupPitch;
+    Tw<true> tw; tw.load(u);
+    const SweepLane sl = make_sweep_lane(u);
+    const int n_sym = fr.n_sym;
+    const int n_pass = 1 + (n_sym > 2 ? (n_sym + 1) / 4 : 0);
+    SweepTotals t = {0u, 0u, 0u, 0.f};
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int sym = pass == 0 ? grp - 2 : 2 + (pass - 1) * 4 + grp;     // < 0: LTS half
+        const bool active = sym < n_sym;
+        const int n0 = sym < 0 ? 32 + 64 * grp : 176 + 80 * sym;           // Channel_Estimation :837-838, CP strip :1028
+        float z[8];
+        if (NOISE == kNoisePhilox && active) {
+            const int base = window_block_base(n0) + u;
+            float za[4], zb[4];
+            philox_normals4(fr.seed, fr.stream, fr.frame_id, (uint32_t)base, kDomainNoise, za);
+            philox_normals4(fr.seed, fr.stream, fr.frame_id, (uint32_t)(base + 8), kDomainNoise, zb);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
+        }
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = slot_m<true>(i);
+            float2 sm = make_float2(0.f, 0.f);
+            if (active) {
+                sm = fr.x[n0 + u + 8 * m];
+                if (NOISE == kNoiseInject) sm.x = add_noise<true>(sm.x, fr.g[n0 + u + 8 * m], fr.sigma_d, 0.f);
+                if (NOISE == kNoisePhilox) sm.x = add_noise<true>(sm.x, z[m], fr.sigma_d, 0.f);
+            }
+            v[i] = sm;
+        }
+        fft64<true>(v, tw, tile, u);
+        if (pass == 0 && grp < 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lts[grp * kWin + u + 8 * j] = v[j];
+        }
+        __syncwarp();
+        if (sym >= 0 && active) {
+            const uint32_t *w = fr.bits + sym * 3;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            uint32_t pk = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t d = ((j < 4 ? sl.dlo : sl.dhi) >> (8 * (j & 3))) & 0xFFu;
+                const float sc = ((sl.lnul >> j) & 1u) ? 0.f : (((sl.lneg >> j) & 1u) ? -0.5f : 0.5f);
+                const float2 A = lts[u + 8 * j], B = lts[kWin + u + 8 * j];
+                const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), sc), __fmul_rn(__fadd_rn(A.y, B.y), sc));      // :848
+                pk += process_bin_hot<true>(v[j], Hh, sc, bit_pair(w0, w1, w2, (int)d), d < 0x80u, t.e2);
+            }
+            t.i += pk & 0xFFu; t.q += (pk >> 8) & 0xFFu; t.both += pk >> 16;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) atomicAdd(&g_replayed_frames, 1ull);
+    return t;
+}
+
+template <int ARITH, int NOISE>
+__global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
+{
+    constexpr bool EXACT = ARITH == kArithExact, CHECKED = ARITH == kArithChecked, EXACT_CHANNEL = EXACT || CHECKED;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
+    __shared__ double s_sum[kWarpsPerBlock][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);                  // same value, provably warp-uniform
+    using SW = StreamWarp<NOISE == kNoiseInject>;
+    using SS = StreamStage<NOISE == kNoiseInject>;
+    SW &ws = reinterpret_cast<SW *>(s_raw)[warp];
+    SW &ws_u = reinterpret_cast<SW *>(s_raw)[warp_u];
+    float2 *tile = ws.tile + grp * kGroupPitch;
+    Tw<EXACT> tw; tw.load(u);
+    const ItemConst ic = make_items(lane);
+    const int n_sym = p.n_sym, len = 160 + 80 * n_sym;
+    const int n_pass = 1 + (n_sym > 2 ? (n_sym + 1) / 4 : 0);
+    const long stride = (long)gridDim.x * kWarpsPerBlock;
+    const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp_u;
+    const long my_frames = f_first < p.n_frames ? (p.n_frames - f_first + stride - 1) / stride : 0;
+    const double q = (double)kQpsk;
+    const double ref2_frame = 48.0 * n_sym * (2.0 * q * q);
+    const float inv_ref2 = (float)(1.0 / ref2_frame);
+
+    const uint32_t stage0 = tma::saddr(&ws_u.st[0]);
+    const uint32_t bar0 = tma::saddr(&ws_u.bar[0]);
+    // refill stage s with pass `pass` of this warp's frame number jf: only the windows that exist are fetched
+    auto issue = [&](long jf, int pass, int s) {
+        if (tma::elect_one()) {
+            const long f = f_first + jf * stride;
+            const int first_sym = pass == 0 ? 0 : 2 + 4 * (pass - 1);
+            const int left = n_sym - first_sym;
+            const int nwin = pass == 0 ? 2 + (left < 2 ? left : 2) : (left < 4 ? left : 4);
+            const int n0 = pass == 0 ? 32 : 176 + 80 * first_sym, n1 = pass == 0 ? 96 : n0 + 80;
+            const int n2 = pass == 0 ? 176 : n0 + 160, n3 = n2 + 80;
+            const uint32_t bar = bar0 + 8u * (uint32_t)s;
+            const uint32_t dst = stage0 + (uint32_t)s * (uint32_t)sizeof(SS);
+            const char *x = reinterpret_cast<const char *>(p.in) + f * ((long)len * 8);
+            tma::expect_tx_addr(bar, (uint32_t)nwin * (NOISE == kNoiseInject ? 768u : 512u));
+            tma::bulk_addr(dst + 0 * kWin * 8, x + n0 * 8, 512, bar);
+            if (nwin > 1) tma::bulk_addr(dst + 1 * kWin * 8, x + n1 * 8, 512, bar);
+            if (nwin > 2) tma::bulk_addr(dst + 2 * kWin * 8, x + n2 * 8, 512, bar);
+            if (nwin > 3) tma::bulk_addr(dst + 3 * kWin * 8, x + n3 * 8, 512, bar);
+            if (NOISE == kNoiseInject) {
+                const char *g = reinterpret_cast<const char *>(p.g) + f * ((long)len * 4);
+                const uint32_t gd = dst + 4 * kWin * 8;
+                tma::bulk_addr(gd + 0 * kWin * 4, g + n0 * 4, 256, bar);
+                if (nwin > 1) tma::bulk_addr(gd + 1 * kWin * 4, g + n1 * 4, 256, bar);
+                if (nwin > 2) tma::bulk_addr(gd + 2 * kWin * 4, g + n2 * 4, 256, bar);
+                if (nwin > 3) tma::bulk_addr(gd + 3 * kWin * 4, g + n3 * 4, 256, bar);
+            }
+        }
+    };
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) tma::mbar_init(&ws.bar[s], 1);
+        tma::fence_mbar_init();
+    }
+    __syncwarp();
+    // the unit to refill next: (frame number, pass)
+    long jf_issue = 0; int pass_issue = 0;
+    auto issue_next = [&](int s) {
+        if (jf_issue < my_frames) {
+            issue(jf_issue, pass_issue, s);
+            if (++pass_issue == n_pass) { pass_issue = 0; ++jf_issue; }
+        }
+    };
+    for (int s = 0; s < kStages; ++s) issue_next(s);
+
+    uint32_t a_i = 0, a_q = 0, a_both = 0, a_ferr = 0, a_frames = 0;
+    double a_e2 = 0.0, a_evm = 0.0;
+    uint32_t k = 0;                                        // units consumed (ring position)
+    for (long j_chunk = 0; j_chunk < my_frames; j_chunk += 32) {
+        double sig_mine = 0.0;
+        if (NOISE != kNoiseNone) {
+            const long jl = j_chunk + lane;
+            if (jl < my_frames) sig_mine = __dsqrt_rn((double)__fdiv_rn(p.power[f_first + jl * stride], p.snr_lin));   // :647, :651
+        }
+        float c_e2 = 0.f, c_evm = 0.f;
+        for (int kk = 0; kk < 32; ++kk) {
+            const long jf = j_chunk + kk;
+            if (jf >= my_frames) break;
+            const long f = f_first + jf * stride;
+            const double sigma_d = NOISE != kNoiseNone ? __shfl_sync(0xffffffffu, sig_mine, kk) : 0.0;
+            const float sigma_f = (float)sigma_d;
+            const uint32_t *fbits = p.tx_bits + f * ((long)n_sym * 3);
+            uint32_t f_i = 0, f_q = 0, f_both = 0;
+            float f_e2 = 0.f, rH2 = 0.f, den_min4 = 0.f;
+            bool doubt = false;
+            for (int pass = 0; pass < n_pass; ++pass, ++k) {
+                const int s = (int)(k & 1u);
+                const uint32_t phase = (k >> 1) & 1u;
+                const int sym = pass == 0 ? grp - 2 : 2 + (pass - 1) * 4 + grp;     // < 0: LTS half
+                const bool active = sym < n_sym;
+                float z[8];
+                if (NOISE == kNoisePhilox && active) {
+                    const int blk = window_block_base(sym < 0 ? 32 + 64 * grp : 176 + 80 * sym) + u;
+                    float za[4], zb[4];
+                    philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)blk, kDomainNoise, za);
+                    philox_normals4(p.seed, p.stream, p.frame0 + (uint64_t)f, (uint32_t)(blk + 8), kDomainNoise, zb);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
+                }
+                // this pass's payload words for the lane's items (used after the transform): round 0 and, from pass 1 on, round 1
+                const int first_sym = pass == 0 ? 0 : 2 + (pass - 1) * 4;
+                uint32_t wq[6];
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const int isym = first_sym + 2 * (t / 3) + (ic.f_off[t % 3] < kWin ? 0 : 1);
+                    wq[t] = (isym < n_sym && (t < 3 || pass > 0)) ? fbits[(first_sym + 2 * (t / 3)) * 3 + ic.word[t % 3]] : 0u;
+                }
+                tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
+                float2 v[8];
+                float n2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int m = slot_m<EXACT>(i);
+                    float2 smp = make_float2(0.f, 0.f);
+                    if (active) {
+                        smp = ws.st[s].x[grp][u + 8 * m];
+                        if (NOISE == kNoiseInject) smp.x = add_noise<EXACT_CHANNEL>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
+                        if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT_CHANNEL>(smp.x, z[m], sigma_d, sigma_f);
+                    }
+                    if (CHECKED) n2 = fmaf(smp.x, smp.x, fmaf(smp.y, smp.y, n2));
+                    v[i] = smp;
+                }
+                __syncwarp();                                     // every lane has its samples: the stage can be refilled
+                issue_next(s);
+                fft64<EXACT>(v, tw, tile, u);
+                float rad = 0.f;
+                if (CHECKED) rad = window_radius(n2, p.radius_scale);
+                uint32_t pk = 0;
+                if (pass == 0) {
+                    float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) dst[u + 8 * jj] = v[jj];
+                    if (CHECKED && u == 0) ws.radius[grp] = rad;
+                    __syncwarp();
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (CHECKED) {
+                        r4 = *reinterpret_cast<const float4 *>(ws.radius);
+                        rH2 = r4.x + r4.y;                                        // 2 r_H, kept for the frame's later passes
+                        den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const int isym = ic.f_off[t] < kWin ? 0 : 1;              // the item's symbol
+                        const bool valid = isym < n_sym;
+                        const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                        const uint32_t w = wq[t];
+                        float e2 = 0.f;
+                        uint32_t r;
+                        if (CHECKED) {
+                            bool dbt = false;
+                            r = process_bin_checked(ws.tile[ic.f_off[t]], make_float2(A.x + B.x, A.y + B.y), 4.f * ic.sc[t], w >> ic.shift[t],
+                                                    isym == 0 ? r4.z : r4.w, rH2, den_min4, e2, dbt);
+                            doubt = doubt || (valid && dbt);
+                        } else {
+                            const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848
+                            r = item_eval<EXACT>(ws.tile[ic.f_off[t]], Hh, ic.sc[t], w >> ic.shift[t], e2);
+                        }
+                        pk += valid ? r : 0u; f_e2 += valid ? e2 : 0.f;
+                    }
+                } else {
+                    // four symbols: all groups publish F, then the 192 data bins are dealt out in two rounds of three items per
+                    // lane -- the item pattern of round 1 is that of round 0 two symbols (= two windows, six payload words) up
+                    float2 *dst = ws.tile + grp * kWin;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) dst[u + 8 * jj] = v[jj];
+                    if (CHECKED && u == 0) ws.radius[grp] = rad;
+                    __syncwarp();
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (CHECKED) r4 = *reinterpret_cast<const float4 *>(ws.radius);
+#pragma unroll
+                    for (int round = 0; round < 2; ++round) {
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const int isym = ic.f_off[t] < kWin ? 0 : 1;
+                            const bool valid = first_sym + 2 * round + isym < n_sym;
+                            const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
+                            const uint32_t w = wq[3 * round + t];
+                            const float2 F = ws.tile[2 * round * kWin + ic.f_off[t]];
+                            float e2 = 0.f;
+                            uint32_t r;
+                            if (CHECKED) {
+                                bool dbt = false;
+                                const float rF = round == 0 ? (isym == 0 ? r4.x : r4.y) : (isym == 0 ? r4.z : r4.w);
+                                r = process_bin_checked(F, make_float2(A.x + B.x, A.y + B.y), 4.f * ic.sc[t], w >> ic.shift[t], rF, rH2, den_min4, e2, dbt);
+                                doubt = doubt || (valid && dbt);
+                            } else {
+                                const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848
+                                r = item_eval<EXACT>(F, Hh, ic.sc[t], w >> ic.shift[t], e2);
+                            }
+                            pk += valid ? r : 0u; f_e2 += valid ? e2 : 0.f;
+                        }
+                    }
+                }
+                f_i += pk & 0xFFu; f_q += (pk >> 8) & 0xFFu; f_both += pk >> 16;
+                __syncwarp();
+            }
+            if (CHECKED) {
+                if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay the frame exactly
+                    SweepFrame fr;
+                    fr.x = p.in + f * len; fr.g = NOISE == kNoiseInject ? p.g + f * len : nullptr; fr.bits = fbits; fr.n_sym = n_sym;
+                    fr.sigma_d = sigma_d; fr.seed = p.seed; fr.stream = p.stream; fr.frame_id = p.frame0 + (uint64_t)f;
+                    const SweepTotals t = sweep_frame_replay<NOISE>(fr, ws.tile, &ws.lts[0][0]);
+                    f_i = t.i; f_q = t.q; f_both = t.both; f_e2 = t.e2;
+                }
+            }
+            const bool any_err = __any_sync(0xffffffffu, (f_i | f_q) != 0u);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) f_e2 += __shfl_xor_sync(0xffffffffu, f_e2, o);
+            float evm;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(evm) : "f"(f_e2 * inv_ref2));                                              // :1124
+            a_i += f_i; a_q += f_q; a_both += f_both;
+            a_ferr += any_err; a_frames += 1;
+            c_e2 += f_e2; c_evm += evm;
+        }
+        a_e2 += (double)c_e2; a_evm += (double)c_evm;
+    }
+    if (p.counters == nullptr) return;
+    const uint32_t t_i = warp_sum(a_i), t_q = warp_sum(a_q), t_both = warp_sum(a_both);
+    if (lane == 0) {
+        s_cnt[warp][0] = (unsigned long long)t_i + 2ull * t_q - 2ull * t_both;     // bit errors (map of :423-430)
+        s_cnt[warp][1] = (unsigned long long)t_i + t_q;
+        s_cnt[warp][2] = a_ferr; s_cnt[warp][3] = a_frames;
+        s_sum[warp][0] = a_e2; s_sum[warp][1] = a_evm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long c[4] = {0, 0, 0, 0}; double sm[2] = {0, 0};
+        for (int w = 0; w < kWarpsPerBlock; ++w) {
+            for (int i = 0; i < 4; ++i) c[i] += s_cnt[w][i];
+            for (int i = 0; i < 2; ++i) sm[i] += s_sum[w][i];
+        }
+        if (c[3] != 0) {
+            ofdm_counters *o = p.counters;
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->bit_errors), c[0]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->rail_errors), c[1]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames_in_error), c[2]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames), c[3]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&o->bits), c[3] * 96ull * (unsigned long long)n_sym);
+            atomicAdd(&o->sum_err2, sm[0]);
+            atomicAdd(&o->sum_ref2, (double)c[3] * ref2_frame);
+            atomicAdd(&o->sum_evm_lin, sm[1]);
+        }
+    }
+}
+
 template <int NOISE> inline size_t stream_smem_bytes() { return sizeof(StreamWarp<NOISE == kNoiseInject>) * kWarpsPerBlock; }
 
 }  // namespace ofdm

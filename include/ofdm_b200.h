@@ -101,6 +101,7 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *                            speculating in fp32, verifying, and replaying doubtful frames exactly (default 1;
  *                            both give the same error counts)
  *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path)
+ *   "general_stream"    = 1  two-symbol frames also take the multi-pass streaming kernel that serves every other frame shape
  *   "multipath_path"    = 0  ofdm_mc_sweep_multipath_dev picks the faster of its two implementations per mode (default);
  *                       = 1  frames staged in HBM (TX, fading, power, one receiver kernel per SNR point);
  *                       = 2  the fused on-chip kernel; both give the same totals */

@@ -228,3 +228,60 @@ def test_monte_carlo_kernel_checked(knobs, pkg):
         assert abs(z.sum_err2 - y.sum_err2) <= 1e-12 * y.sum_err2
     assert runs["replay_all"][1] == n * len(snr) and runs["all_exact"][1] == 0
     assert 0 < runs["checked"][1] < n * len(snr) // 10
+
+
+@pytest.mark.parametrize("n_sym,snr", [(1, 1.0), (3, 5.0), (4, 0.0), (6, 2.0), (7, 9.0), (9, 3.0), (23, 4.0)])
+def test_other_frame_shapes(knobs, pkg, port, n_sym, snr):
+    """frames with n_sym != 2 stream through k_stream_rxn (pass 0 = LTS + two symbols, then four symbols per pass): speculation
+    on / off / forced replay, the generic kernel and the oracle agree; fast mode agrees with the generic fast kernel"""
+    ofdm = knobs
+    n_frames = 1200
+    bits, g = bits_and_noise(900 + n_sym, n_frames, n_sym)
+    packed = ofdm.to_dev(pkg.pack_bits_host(bits).view(np.int32))
+    gd = ofdm.to_dev(g)
+    frames, power = ofdm.tx_frames(packed, n_sym, pkg.MODE_EXACT)
+    res = run_variants(ofdm, pkg, lambda: ofdm.awgn_rx_inject(frames, gd, packed, snr, n_sym, pkg.MODE_EXACT, power=power)[0])
+    acc = port.chain(bits, g, n_sym, snr)
+    want = (acc.bit_errors, acc.bits, acc.frames_in_error, acc.rail_errors, acc.frames)
+    for name, (c, _) in res.items():
+        assert ints(c) == want, name
+        assert abs(c.sum_err2 - acc.sum_err2) <= 1e-5 * acc.sum_err2, name
+    assert res["replay_all"][1] == n_frames and res["all_exact"][1] == 0 and res["checked"][1] < n_frames // 2
+    for option in (0, 1):
+        ofdm.set_option("force_generic_rx", option)
+        c = ofdm.awgn_rx_inject(frames, gd, packed, snr, n_sym, pkg.MODE_FAST, power=power)[0]
+        if option == 0:
+            fast_stream = c
+        else:
+            assert ints(c) == ints(fast_stream)
+    ofdm.set_option("force_generic_rx", 0)
+    # noise-free OTA frames and on-chip Philox noise through the same kernel
+    ota = ofdm.awgn_inject(frames, gd, snr, n_sym, pkg.MODE_EXACT, power=power)
+    a = ofdm.rx_frames(ota, packed, n_sym, pkg.MODE_EXACT)[0]
+    assert ints(a) == want
+    p1 = ofdm.awgn_rx_philox(frames, packed, snr, 3, 1, 50, n_sym, pkg.MODE_EXACT, power=power)[0]
+    ofdm.set_option("force_generic_rx", 1)
+    p2 = ofdm.awgn_rx_philox(frames, packed, snr, 3, 1, 50, n_sym, pkg.MODE_EXACT, power=power)[0]
+    assert ints(p1) == ints(p2)
+
+
+def test_general_stream_kernel_on_the_default_shape(knobs, pkg):
+    """the multi-pass kernel restricted to pass 0 must reproduce k_stream_rx2 on two-symbol frames"""
+    ofdm = knobs
+    import torch
+    n, n_sym = 200_000, 2
+    gen = torch.Generator(device=ofdm.device); gen.manual_seed(12)
+    packed = torch.randint(-2**31, 2**31 - 1, (n * 6,), dtype=torch.int32, device=ofdm.device, generator=gen)
+    g = torch.randn((n, 320), dtype=torch.float32, device=ofdm.device, generator=gen)
+    frames, power = ofdm.tx_frames(packed, n_sym, pkg.MODE_EXACT)
+    try:
+        for mode in (pkg.MODE_EXACT, pkg.MODE_FAST):
+            for snr in (1.0, 9.0):
+                ofdm.set_option("general_stream", 0)
+                a = ofdm.awgn_rx_inject(frames, g, packed, snr, n_sym, mode, power=power)[0]
+                ofdm.set_option("general_stream", 1)
+                b = ofdm.awgn_rx_inject(frames, g, packed, snr, n_sym, mode, power=power)[0]
+                assert ints(a) == ints(b)
+                assert abs(a.sum_err2 - b.sum_err2) <= 1e-6 * b.sum_err2 and abs(a.sum_evm_lin - b.sum_evm_lin) <= 1e-6 * b.sum_evm_lin
+    finally:
+        ofdm.set_option("general_stream", 0)
