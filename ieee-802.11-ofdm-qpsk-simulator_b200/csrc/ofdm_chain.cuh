@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
     const int n_pass = 1 + (n_sym > 2 ? (n_sym + 1) / 4 : 0);
     const long stride = (long)gridDim.x * kWarpsPerBlock;
     const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp_u;
-    const long my_frames = f_first < p.n_frames ? (p.n_frames - f_first + stride - 1) / stride : 0;
+    const int my_frames = f_first < p.n_frames ? (int)((p.n_frames - f_first + stride - 1) / stride) : 0;   // < 2^31 by a wide margin
     const double q = (double)kQpsk;
     const double ref2_frame = 48.0 * n_sym * (2.0 * q * q);
     const float inv_ref2 = (float)(1.0 / ref2_frame);
@@ -902,9 +902,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
     const uint32_t stage0 = tma::saddr(&ws_u.st[0]);
     const uint32_t bar0 = tma::saddr(&ws_u.bar[0]);
     // refill stage s with pass `pass` of this warp's frame number jf: only the windows that exist are fetched
-    auto issue = [&](long jf, int pass, int s) {
+    auto issue = [&](int jf, int pass, int s) {
         if (tma::elect_one()) {
-            const long f = f_first + jf * stride;
+            const long f = f_first + (long)jf * stride;
             const int first_sym = pass == 0 ? 0 : 2 + 4 * (pass - 1);
             const int left = n_sym - first_sym;
             const int nwin = pass == 0 ? 2 + (left < 2 ? left : 2) : (left < 4 ? left : 4);
@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
     }
     __syncwarp();
     // the unit to refill next: (frame number, pass)
-    long jf_issue = 0; int pass_issue = 0;
+    int jf_issue = 0, pass_issue = 0;
     auto issue_next = [&](int s) {
         if (jf_issue < my_frames) {
             issue(jf_issue, pass_issue, s);
@@ -946,22 +946,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
     uint32_t a_i = 0, a_q = 0, a_both = 0, a_ferr = 0, a_frames = 0;
     double a_e2 = 0.0, a_evm = 0.0;
     uint32_t k = 0;                                        // units consumed (ring position)
-    for (long j_chunk = 0; j_chunk < my_frames; j_chunk += 32) {
+    for (int j_chunk = 0; j_chunk < my_frames; j_chunk += 32) {
         double sig_mine = 0.0;
         if (NOISE != kNoiseNone) {
-            const long jl = j_chunk + lane;
-            if (jl < my_frames) sig_mine = __dsqrt_rn((double)__fdiv_rn(p.power[f_first + jl * stride], p.snr_lin));   // :647, :651
+            const int jl = j_chunk + lane;
+            if (jl < my_frames) sig_mine = __dsqrt_rn((double)__fdiv_rn(p.power[f_first + (long)jl * stride], p.snr_lin));   // :647, :651
         }
         float c_e2 = 0.f, c_evm = 0.f;
         for (int kk = 0; kk < 32; ++kk) {
-            const long jf = j_chunk + kk;
+            const int jf = j_chunk + kk;
             if (jf >= my_frames) break;
-            const long f = f_first + jf * stride;
+            const long f = f_first + (long)jf * stride;
             const double sigma_d = NOISE != kNoiseNone ? __shfl_sync(0xffffffffu, sig_mine, kk) : 0.0;
             const float sigma_f = (float)sigma_d;
             const uint32_t *fbits = p.tx_bits + f * ((long)n_sym * 3);
             uint32_t f_i = 0, f_q = 0, f_both = 0;
-            float f_e2 = 0.f, rH2 = 0.f, den_min4 = 0.f;
+            float f_e2 = 0.f, rH2 = 0.f;
             bool doubt = false;
             for (int pass = 0; pass < n_pass; ++pass, ++k) {
                 const int s = (int)(k & 1u);
@@ -1016,8 +1016,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                     if (CHECKED) {
                         r4 = *reinterpret_cast<const float4 *>(ws.radius);
                         rH2 = r4.x + r4.y;                                        // 2 r_H, kept for the frame's later passes
-                        den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
                     }
+                    const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         const int isym = ic.f_off[t] < kWin ? 0 : 1;              // the item's symbol
@@ -1047,6 +1047,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                     __syncwarp();
                     float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (CHECKED) r4 = *reinterpret_cast<const float4 *>(ws.radius);
+                    const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
 #pragma unroll
                     for (int round = 0; round < 2; ++round) {
 #pragma unroll
