@@ -54,6 +54,15 @@ def test_sweep_routes_agree_full_size(ofdm, pkg):
     host = ofdm.sweep_inject_host(bits.cpu().numpy(), g.cpu().numpy(), N, NSYM, SNRS, pkg.MODE_EXACT)
     for w, h in zip(whole, host):
         assert ints(w) == ints(h)
+    # the speculating EXACT kernel (default) == the reference's arithmetic on every frame, 21 x 192 M rail decisions
+    ofdm.set_option("exact_speculation", 0)
+    try:
+        all_exact = ofdm.sweep_inject_dev(bits, g, N, NSYM, SNRS, pkg.MODE_EXACT)
+    finally:
+        ofdm.set_option("exact_speculation", 1)
+    for w, e in zip(whole, all_exact):
+        assert ints(w) == ints(e)
+        assert abs(w.sum_err2 - e.sum_err2) <= 1e-6 * e.sum_err2
     # fast mode differs from exact only by decisions within fp32 rounding of zero
     fast = ofdm.sweep_inject_dev(bits, g, N, NSYM, SNRS, pkg.MODE_FAST)
     for w, f in zip(whole, fast):
