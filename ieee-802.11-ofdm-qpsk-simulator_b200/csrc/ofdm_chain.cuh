@@ -979,11 +979,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                 }
                 // this pass's payload words for the lane's items (used after the transform): round 0 and, from pass 1 on, round 1
                 const int first_sym = pass == 0 ? 0 : 2 + (pass - 1) * 4;
-                uint32_t wq[6];
+                const uint32_t *fb = fbits + first_sym * 3;
+                const int left = pass == 0 ? (n_sym < 2 ? n_sym : 2) : n_sym - first_sym;     // symbols this pass decides
+                uint32_t wq[6], vmask = 0;                                                   // bit t: item t of this pass exists
 #pragma unroll
-                for (int t = 0; t < 6; ++t) {
-                    const int isym = first_sym + 2 * (t / 3) + (ic.f_off[t % 3] < kWin ? 0 : 1);
-                    wq[t] = (isym < n_sym && (t < 3 || pass > 0)) ? fbits[(first_sym + 2 * (t / 3)) * 3 + ic.word[t % 3]] : 0u;
+                for (int t = 0; t < 3; ++t) {
+                    const int s01 = ic.f_off[t] < kWin ? 0 : 1;
+                    const bool v0 = s01 < left, v1 = 2 + s01 < left;
+                    wq[t] = v0 ? fb[ic.word[t]] : 0u;
+                    wq[3 + t] = v1 ? fb[6 + ic.word[t]] : 0u;
+                    vmask |= (uint32_t)v0 << t | (uint32_t)v1 << (3 + t);
                 }
                 tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
                 float2 v[8];
@@ -1021,7 +1026,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         const int isym = ic.f_off[t] < kWin ? 0 : 1;              // the item's symbol
-                        const bool valid = isym < n_sym;
+                        const bool valid = (vmask >> t) & 1u;
                         const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
                         const uint32_t w = wq[t];
                         float e2 = 0.f;
@@ -1053,7 +1058,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
 #pragma unroll
                         for (int t = 0; t < 3; ++t) {
                             const int isym = ic.f_off[t] < kWin ? 0 : 1;
-                            const bool valid = first_sym + 2 * round + isym < n_sym;
+                            const bool valid = (vmask >> (3 * round + t)) & 1u;
                             const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
                             const uint32_t w = wq[3 * round + t];
                             const float2 F = ws.tile[2 * round * kWin + ic.f_off[t]];
