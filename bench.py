@@ -241,6 +241,24 @@ def run_extras(o, pkg, torch, dev, args, rank, world):
         out["cfg3_mc_philox_" + name] = {"frames": nm, "snr_points": len(SNRS), "ms": ms,
                                          "symbols_per_s": nm * N_SYM * len(SNRS) / (ms * 1e-3),
                                          "fft_gflops": nm * len(SNRS) * 4 * 1920 / (ms * 1e-3) / 1e9}
+    # other frame shapes (n_sym != 2) through the multi-pass streaming receiver, injected draws, 4 M windows each
+    shapes = {}
+    for ns in (1, 4, 16):
+        nf = 4_000_000 // (2 + ns)
+        fl = 160 + 80 * ns
+        b = torch.randint(-2 ** 31, 2 ** 31 - 1, (nf * 3 * ns,), dtype=torch.int32, device=dev)
+        fr = torch.empty((nf, fl, 2), dtype=torch.float32, device=dev)
+        gg = torch.randn((nf, fl), dtype=torch.float32, device=dev)
+        pw = torch.empty((nf,), dtype=torch.float32, device=dev)
+        for mode, name in ((pkg.MODE_EXACT, "exact"), (pkg.MODE_FAST, "fast")):
+            o._check(lib.ofdm_tx_frames(h, b.data_ptr(), fr.data_ptr(), pw.data_ptr(), nf, ns, mode))
+            ms = timed(lambda: o._check(lib.ofdm_awgn_rx_inject(h, fr.data_ptr(), gg.data_ptr(), pw.data_ptr(), b.data_ptr(), 8.0, nf, ns, mode,
+                                                                  cnt.data_ptr(), None)), reps=3)
+            shapes["n_sym_%d_%s" % (ns, name)] = {"frames": nf, "ms": ms, "data_symbols_per_s": nf * ns / (ms * 1e-3),
+                                                  "windows_per_s": nf * (2 + ns) / (ms * 1e-3)}
+        del b, fr, gg, pw
+    out["other_frame_shapes_rx"] = shapes
+    torch.cuda.empty_cache()
     out["next_rows_full_receiver_path"] = run_next_rows(o, pkg, torch, dev, peak)
     torch.cuda.empty_cache()
     # configs[4]: per-frame random multipath (8 taps drawn on chip) + LTS estimate + ZF equaliser, Philox noise;
