@@ -36,3 +36,39 @@ for seed in range(seeds):
         print("seed %d snr %5.1f: bit errors %11d  replayed %7d (%.3f%%)  totals equal %s  sum_err2 rel diff %.1e"
               % (seed, snr, int(a[0]), res[0][1], 100.0 * res[0][1] / n, same, abs(e2a / e2b - 1)), flush=True)
 print("decisions compared: %.3e  launches with different totals: %d  replayed frames: %d" % (decisions, mismatches, replays))
+
+# the same comparison on fading channels (configs[4]: 8 random taps per frame, on-chip Philox noise, HBM-staged path) and on
+# other frame shapes (multi-pass streaming receiver)
+snr21 = [float(s) for s in range(0, 21)]
+for seed in range(seeds):
+    res = []
+    for spec in (1, 0):
+        o.set_option("exact_speculation", spec); o.set_option("multipath_path", 1)
+        o.replayed_frames(reset=True)
+        c = o.mc_sweep_multipath(100 + seed, 0, n, 2, 8, snr21, pkg.MODE_EXACT)
+        res.append(([(x.bit_errors, x.bits, x.frames_in_error, x.rail_errors, x.frames) for x in c], [x.sum_err2 for x in c], o.replayed_frames()))
+    same = res[0][0] == res[1][0]
+    worst = max(abs(a / b - 1) for a, b in zip(res[0][1], res[1][1]))
+    print("multipath seed %d: %d frames x 21 SNR points, replayed %d (%.2f%%), totals equal %s, worst sum_err2 rel diff %.1e"
+          % (seed, n, res[0][2], 100.0 * res[0][2] / (n * 21), same, worst), flush=True)
+o.set_option("multipath_path", 0)
+for n_sym in (1, 3, 5, 12):
+    nf = n // (2 + n_sym) * 4
+    gen = torch.Generator(device=dev); gen.manual_seed(77 + n_sym)
+    b = torch.randint(-2**31, 2**31 - 1, (nf * 3 * n_sym,), dtype=torch.int32, device=dev, generator=gen)
+    gg = torch.randn((nf, 160 + 80 * n_sym), dtype=torch.float32, device=dev, generator=gen)
+    fr = torch.empty((nf, 160 + 80 * n_sym, 2), dtype=torch.float32, device=dev)
+    pw = torch.empty((nf,), dtype=torch.float32, device=dev)
+    lib.ofdm_tx_frames(h, b.data_ptr(), fr.data_ptr(), pw.data_ptr(), nf, n_sym, pkg.MODE_EXACT)
+    for snr in (0.0, 4.0, 8.0):
+        res = []
+        for spec in (1, 0):
+            o.set_option("exact_speculation", spec)
+            cnt.zero_(); o.replayed_frames(reset=True)
+            o._check(lib.ofdm_awgn_rx_inject(h, fr.data_ptr(), gg.data_ptr(), pw.data_ptr(), b.data_ptr(), snr, nf, n_sym, pkg.MODE_EXACT, cnt.data_ptr(), None))
+            res.append((cnt.cpu().numpy().reshape(-1).copy(), o.replayed_frames()))
+        a, bb = res[0][0], res[1][0]
+        print("n_sym %2d snr %4.1f: %d frames, replayed %d, totals equal %s, sum_err2 rel diff %.1e"
+              % (n_sym, snr, nf, res[0][1], bool((a[:5] == bb[:5]).all()), abs(a.view(np.float64)[5] / bb.view(np.float64)[5] - 1)), flush=True)
+    del b, gg, fr, pw
+o.set_option("exact_speculation", 1)
