@@ -406,11 +406,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 }
                 __syncwarp();
             }
+            pk = __reduce_add_sync(0xffffffffu, pk);                // one REDUX: the three 8-bit fields stay below 97
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                pk += __shfl_xor_sync(0xffffffffu, pk, o);
-                e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-            }
+            for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
             float evm;
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(evm) : "f"(e2 * inv_ref2));                 // :1124
             if (lane == (si & 31)) {                                   // the lane that owns this SNR point books the frame
