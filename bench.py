@@ -276,7 +276,7 @@ def run_next_rows(o, pkg, torch, dev, peak, n=32768):
     x10 repetition, AWGN over all 9800 samples, capture window, packet detection / selection, matched filter + decimation,
     coarse + fine CFO, receiver).  Per stage: time (CUDA events) and algorithmic bytes (what the stage must read + write)."""
     def timed(fn, reps=3):
-        out = fn(); torch.cuda.synchronize()
+        out = fn(); out = fn(); torch.cuda.synchronize()        # twice: the stage outputs ping-pong between two cached allocations
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):

@@ -993,9 +993,8 @@ int ofdm_gather(ofdm_ctx *ctx, const float *in, const int32_t *start, int start_
     OFDM_REQUIRE(ctx, n >= 0 && in_len >= 1 && out_len >= 1 && (start != nullptr || start_scalar >= 0));
     if (n == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && in != out);
-    long total = n * (long)out_len;
-    int grid = (int)((total + 255) / 256 < 4L * ctx->sm_count * 8 ? (total + 255) / 256 : 4L * ctx->sm_count * 8);
-    k_gather<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(in), start, start_scalar, reinterpret_cast<float2 *>(out), n, in_len, out_len);
+    int grid = grid_for(ctx, k_gather, 0, kWarpsPerBlock, n);
+    k_gather<<<grid, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(in), start, start_scalar, reinterpret_cast<float2 *>(out), n, in_len, out_len);
     return check_launch(ctx, "k_gather");
 }
 int ofdm_rrc_rx_idx(ofdm_ctx *ctx, const float *in, const int32_t *idx, float *out, long n_frames, int in_len, int frame_len)

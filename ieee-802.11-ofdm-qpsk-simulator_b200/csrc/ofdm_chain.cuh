@@ -1385,14 +1385,22 @@ __global__ void __launch_bounds__(kThreads) k_cfo(const float2 *__restrict__ rx,
 
 // out[f][j] = in[f][(start_f + j) % in_len], j < out_len: Slice_Repeater (:193) generalised -- prefix slices (:955),
 // tiling (:612: start 0, out_len = r * in_len) and capture windows of the repeated waveform all come out of it.
-__global__ void k_gather(const float2 *__restrict__ in, const int32_t *__restrict__ start, int start_scalar, float2 *__restrict__ out,
-                         long n, int in_len, int out_len)
+// One warp per frame: 32-bit index arithmetic, the wrap kept incrementally (no division per sample).
+__global__ void __launch_bounds__(kThreads) k_gather(const float2 *__restrict__ in, const int32_t *__restrict__ start, int start_scalar,
+                                                     float2 *__restrict__ out, long n, int in_len, int out_len)
 {
-    const long total = n * out_len;
-    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-        const long f = t / out_len; const int j = (int)(t - f * out_len);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int step = 32 % in_len;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n; f += (long)gridDim.x * kWarpsPerBlock) {
         const int s = start != nullptr ? start[f] : start_scalar;
-        out[t] = in[f * in_len + (int)(((long)s + j) % in_len)];
+        const float2 *src = in + f * in_len;
+        float2 *dst = out + f * out_len;
+        int idx = (int)(((long)s + lane) % in_len);
+        for (int j = lane; j < out_len; j += 32) {
+            dst[j] = src[idx];
+            idx += step;
+            if (idx >= in_len) idx -= in_len;
+        }
     }
 }
 // frame -> prefix || frame (the STS slot in front of LTS || data, :572-581)
