@@ -22,6 +22,12 @@ def test_detection_and_selection_match_reference(ofdm, pkg, port, po, golden):
         caps.append(noisy[start:start + 3008])
     caps.append(np.zeros((3008, 2), np.float32))                                   # silence: 0/0 -> NaN -> no detection
     caps.append(rng.standard_normal((3008, 2)).astype(np.float32))                 # noise only
+    # magnitudes that leave the scaled power chain's range (tiny, huge, non-finite): the plain chain must take over
+    for scale in (1e-25, 3e-19, 1e17, 1e20):
+        caps.insert(0, (caps[len(caps) % 7] * np.float32(scale)).astype(np.float32))
+    bad = caps[5].copy(); bad[1000, 0] = np.nan; caps.insert(0, bad)
+    bad = caps[6].copy(); bad[2000, 1] = np.inf; caps.insert(0, bad)
+    mixed = caps[7].copy(); mixed[::3] *= np.float32(1e-24); caps.insert(0, mixed)
     caps = np.stack(caps)
     corr = ofdm.packet_detect(ofdm.to_dev(caps))
     idx = ofdm.packet_select(corr).cpu().numpy()

@@ -1,4 +1,4 @@
-"""One launch of a secondary kernel for ncu: `one_launch.py rxn <n_sym> <exact|fast>` or `one_launch.py mp <exact|fast>`."""
+"""One launch of a secondary kernel for ncu: `one_launch.py rxn <n_sym> <exact|fast>` `one_launch.py mp <exact|fast>` or `one_launch.py detect`."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,6 +17,10 @@ if what == "rxn":
     lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), power.data_ptr(), n, n_sym, mode)
     for _ in range(3):
         lib.ofdm_awgn_rx_inject(h, frames.data_ptr(), g.data_ptr(), power.data_ptr(), bits.data_ptr(), 8.0, n, n_sym, mode, cnt.data_ptr(), None)
+elif what == "detect":
+    cap = torch.randn((32768, 3008, 2), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        o.packet_detect(cap)
 else:
     snr = [float(s) for s in range(21)]
     cnt = o.new_counters(21)
