@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "ofdm_chain.cuh"
@@ -105,7 +106,29 @@ float snr_linear(float snr_db)
     return (float)pow(10.0, (double)(snr_db / 10));
 }
 
-int upload_tables(ofdm_ctx *ctx, const float *lts_time /* nullable */)
+// running float power sum of OFDM.c:637-641 over n samples, with the device's glibc-faithful hypot (one thread: the
+// chain is sequential) -- the same arithmetic k_frame_power_exact continues from
+__global__ void k_power_prefix(const float2 *__restrict__ x, int n, float *__restrict__ out)
+{
+    float p = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const double h = hypot_glibc((double)x[i].x, (double)x[i].y);
+        p = __double2float_rn(__dadd_rn((double)p, __dmul_rn(h, h)));
+    }
+    *out = p;
+}
+
+// __constant__ c_tab is per device, not per context: it is written once per device (first context), under this
+// mutex, before any other context of that device can exist -- a later ofdm_ctx_create never touches it, so it cannot
+// disturb kernels another context has in flight.  The host-side copies of the preambles are cached alongside.
+struct DeviceTables {
+    bool ready = false;
+    float lts_freq[128], lts_time[320], sts_time[320], lts_power_prefix;
+};
+std::mutex g_tables_mutex;
+DeviceTables g_tables[64];
+
+int upload_tables(ofdm_ctx *ctx, const float *lts_time /* nullable */, float power_prefix)
 {
     Tables t;
     memset(&t, 0, sizeof t);
@@ -129,15 +152,9 @@ int upload_tables(ofdm_ctx *ctx, const float *lts_time /* nullable */)
     }
     if (lts_time) {
         memcpy(t.lts_time, lts_time, sizeof t.lts_time);
-        // OFDM.c:637-641 over the LTS slot: float accumulator, double terms cabs*cabs (libm hypot == the reference's cabs)
-        float acc = 0.0f; double sum = 0.0;
-        for (int i = 0; i < 160; ++i) {
-            double h = hypot((double)lts_time[2 * i], (double)lts_time[2 * i + 1]);
-            acc = (float)((double)acc + h * h);
-            sum += (double)lts_time[2 * i] * lts_time[2 * i] + (double)lts_time[2 * i + 1] * lts_time[2 * i + 1];
-        }
-        t.lts_power_prefix = acc;
-        ctx->lts_power_prefix = acc;
+        double sum = 0.0;
+        for (int i = 0; i < 160; ++i) sum += (double)lts_time[2 * i] * lts_time[2 * i] + (double)lts_time[2 * i + 1] * lts_time[2 * i + 1];
+        t.lts_power_prefix = power_prefix;        // OFDM.c:637-641 over the LTS slot, computed on the device (k_power_prefix)
         t.lts_power_sum = (float)sum;
     }
     OFDM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &t, sizeof t, 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -190,13 +207,20 @@ int launch_stream_n(ofdm_ctx *ctx, const RxParams &p)
     k<<<grid, kThreads, smem, ctx->stream>>>(p);
     return check_launch(ctx, "k_stream_rxn");
 }
+// error radii of the speculating EXACT kernels (ofdm_chain.cuh: kRadius, kChanRadius)
+void set_radius(ofdm_ctx *ctx, RxParams &q)
+{
+    q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+    q.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf((float)OFDM_FRAME_LEN(q.n_sym) * q.snr_lin) * 1.001f;
+}
+
 template <int NOISE>
 int launch_stream_n_mode(ofdm_ctx *ctx, int mode, const RxParams &p)
 {
     if (mode != OFDM_MODE_EXACT) return launch_stream_n<kArithFast, NOISE>(ctx, p);
     if (!ctx->checked) return launch_stream_n<kArithExact, NOISE>(ctx, p);
     RxParams q = p;
-    q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+    set_radius(ctx, q);
     return launch_stream_n<kArithChecked, NOISE>(ctx, q);
 }
 
@@ -217,7 +241,7 @@ int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
             // fp32 speculation + verification + exact replay: same counts as the all-exact kernel (ofdm_chain.cuh)
             if (ctx->checked) {
                 RxParams q = p;
-                q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+                set_radius(ctx, q);
                 if (noise == kNoiseNone) return launch_stream<kArithChecked, kNoiseNone>(ctx, q);
                 if (noise == kNoiseInject) return launch_stream<kArithChecked, kNoiseInject>(ctx, q);
                 return launch_stream<kArithChecked, kNoisePhilox>(ctx, q);
@@ -300,11 +324,20 @@ int ofdm_ctx_create(ofdm_ctx **out, int device)
     if (e != cudaSuccess) { delete ctx; return OFDM_ERR_CUDA; }
     ctx->owns_stream = true;
 
-    // LTS: Preamble_Generator(type 1) OFDM.c:368-399 -- frequency grid from L_k at c = 6..58, time slot through
-    // this library's own exact ifft kernel, then [samples 32..63][0..63][0..63]
-    int st = upload_tables(ctx, nullptr);
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    DeviceTables &dt = g_tables[device & 63];
+    int st = OFDM_OK;
     float *d_buf = nullptr;
-    if (st == OFDM_OK && cudaMalloc(&d_buf, 2 * 128 * sizeof(float)) != cudaSuccess) st = OFDM_ERR_NOMEM;
+    if (dt.ready) {                 // the device's tables are in place: nothing is uploaded, nothing running is disturbed
+        memcpy(ctx->lts_freq, dt.lts_freq, sizeof dt.lts_freq);
+        memcpy(ctx->lts_time, dt.lts_time, sizeof dt.lts_time);
+        memcpy(ctx->sts_time, dt.sts_time, sizeof dt.sts_time);
+        ctx->lts_power_prefix = dt.lts_power_prefix;
+    } else {
+    // LTS: Preamble_Generator(type 1) OFDM.c:368-399 -- frequency grid from L_k at c = 6..58, time slot through
+    // this library's own exact ifft kernel (it reads only the twiddles of c_tab), then [samples 32..63][0..63][0..63]
+    st = upload_tables(ctx, nullptr, 0.f);
+    if (st == OFDM_OK && cudaMalloc(&d_buf, (2 * 128 + 320 + 4) * sizeof(float)) != cudaSuccess) st = OFDM_ERR_NOMEM;
     if (st == OFDM_OK) {
         memset(ctx->lts_freq, 0, sizeof ctx->lts_freq);
         for (int i = 0; i < 53; ++i) ctx->lts_freq[2 * (6 + i)] = (float)kLk[i];
@@ -317,7 +350,16 @@ int ofdm_ctx_create(ofdm_ctx **out, int device)
             memcpy(ctx->lts_time, t64 + 64, 32 * 2 * sizeof(float));                 // :396
             memcpy(ctx->lts_time + 64, t64, 64 * 2 * sizeof(float));                 // :397 (first copy)
             memcpy(ctx->lts_time + 64 + 128, t64, 64 * 2 * sizeof(float));           // :397 (second copy)
-            st = upload_tables(ctx, ctx->lts_time);
+            // the exact-mode power prefix of the LTS slot, in the device's own arithmetic (the kernels continue this chain)
+            float *d_lts = d_buf + 256, *d_pref = d_buf + 256 + 320;
+            if (cudaMemcpyAsync(d_lts, ctx->lts_time, sizeof ctx->lts_time, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+            if (st == OFDM_OK) {
+                k_power_prefix<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(d_lts), 160, d_pref);
+                st = check_launch(ctx, "k_power_prefix");
+            }
+            if (st == OFDM_OK && cudaMemcpyAsync(&ctx->lts_power_prefix, d_pref, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+            if (st == OFDM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
+            if (st == OFDM_OK) st = upload_tables(ctx, ctx->lts_time, ctx->lts_power_prefix);
         }
     }
     // STS: Preamble_Generator(type 0) OFDM.c:479-492: S_k * (float)sqrt(13/6) at c = 6..58, exact ifft, first 16 samples x 10 (:393)
@@ -331,11 +373,19 @@ int ofdm_ctx_create(ofdm_ctx **out, int device)
         if (st == OFDM_OK) st = launch_fft<true, true>(ctx, d_buf, d_buf + 128, 1);
         if (st == OFDM_OK && cudaMemcpyAsync(t64, d_buf + 128, sizeof t64, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
         if (st == OFDM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = OFDM_ERR_CUDA;
-        if (st == OFDM_OK) {
-            for (int r = 0; r < 10; ++r) memcpy(ctx->sts_time + 32 * r, t64, 16 * 2 * sizeof(float));
-            if (cudaMalloc(&ctx->sts_dev, sizeof ctx->sts_time) != cudaSuccess) st = OFDM_ERR_NOMEM;
-            else if (cudaMemcpy(ctx->sts_dev, ctx->sts_time, sizeof ctx->sts_time, cudaMemcpyHostToDevice) != cudaSuccess) st = OFDM_ERR_CUDA;
-        }
+        if (st == OFDM_OK) for (int r = 0; r < 10; ++r) memcpy(ctx->sts_time + 32 * r, t64, 16 * 2 * sizeof(float));
+    }
+    if (st == OFDM_OK) {
+        memcpy(dt.lts_freq, ctx->lts_freq, sizeof dt.lts_freq);
+        memcpy(dt.lts_time, ctx->lts_time, sizeof dt.lts_time);
+        memcpy(dt.sts_time, ctx->sts_time, sizeof dt.sts_time);
+        dt.lts_power_prefix = ctx->lts_power_prefix;
+        dt.ready = true;
+    }
+    }
+    if (st == OFDM_OK) {            // per-context device copy of the STS slot (ofdm_prepend_sts)
+        if (cudaMalloc(&ctx->sts_dev, sizeof ctx->sts_time) != cudaSuccess) st = OFDM_ERR_NOMEM;
+        else if (cudaMemcpy(ctx->sts_dev, ctx->sts_time, sizeof ctx->sts_time, cudaMemcpyHostToDevice) != cudaSuccess) st = OFDM_ERR_CUDA;
     }
     if (d_buf) cudaFree(d_buf);
     if (st != OFDM_OK) { ofdm_ctx_destroy(ctx); return st; }
@@ -759,6 +809,7 @@ int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long
         for (int i = 0; i < n_snr; ++i) { p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i])); }
         const size_t smem = mc_smem_bytes();
         p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+        p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
         auto launch = [&](auto k) -> int {
             OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int grid = grid_for(ctx, k, smem, kWarpsPerBlock, n_frames);
@@ -858,6 +909,7 @@ int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, l
         p.seed = seed; p.frame0 = frame0; p.n_frames = n_frames; p.n_snr = n_snr; p.counters = counters; p.n_taps = n_taps;
         for (int i = 0; i < n_snr; ++i) { p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i])); }
         p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+        p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
         const size_t smem = mc_smem_bytes(true);
         auto launch = [&](auto k) -> int {
             OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

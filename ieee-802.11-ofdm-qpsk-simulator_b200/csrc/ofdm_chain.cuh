@@ -74,21 +74,30 @@ __device__ __forceinline__ uint32_t item_eval(float2 F, float2 Hh, float sc, uin
 // of the equaliser (:1050) moves by at most |dF| |H|_1 + |dH| |F|_1 + |dF||dH|, and its fp32 evaluation errs by
 // 2^-23 |F|_1 |H|_1 more (process_bin_hot).  The decision (:860-868) is the sign of the reference's numerator
 // whenever the quotient cannot underflow, which the magnitude guards below ensure.
+//
+// The channel is speculated too (round 2): the kernel adds the noise as fma(sigma_f, g, x) with sigma_f = (float)sigma_d,
+// the reference as fl32(x + fl32(sigma_d * g)) (:651).  Per sample the two differ by at most 2u |sigma g| + 2u |x'|
+// (rounding of sigma, of the product, of the two sums), so for a window |delta|_2 <= 2u |sigma g|_2 + 2u |x'|_2
+// <= 4u |x'|_2 + 2u |x|_2 with x the clean samples, and the transform maps it to at most 8 |delta|_2 in any bin:
+// 32 u |x'|_2, charged to kRadius (97 + 272 + 32 + 32 = 433 <= 512), plus 16 u |x|_2 <= 16 u sqrt(len * P), P the
+// frame's mean power of :637-643 -- the kChanRadius term (18 u, margin included), which does not depend on the window.
 enum { kArithFast = 0, kArithExact = 1, kArithChecked = 2 };
 constexpr float kRadius = 512.f * 5.9604645e-8f;
+constexpr float kChanRadius = 18.f * 5.9604645e-8f;
 
 __device__ unsigned long long g_replayed_frames;     // frames the checked kernels replayed exactly (statistics)
 
 // radius of one window from the lane's share of sum |x|^2; windows whose energy is outside [1e-30, 1e20] are never
 // trusted (squares may have underflowed / the magnitude guards of the decision would not hold)
-__device__ __forceinline__ float window_radius(float n2, float scale)
+__device__ __forceinline__ float window_radius(float2 n2v, float scale, float extra)
 {
+    float n2 = n2v.x + n2v.y;
     n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
     n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
     n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));          // flushing is harmless: n2 < 1e-30 is rejected
-    return (n2 >= 1e-30f && n2 < 1e20f) ? scale * r : __int_as_float(0x7f800000);
+    return (n2 >= 1e-30f && n2 < 1e20f) ? fmaf(scale, r, extra) : __int_as_float(0x7f800000);
 }
 
 // One data bin, speculated: like process_bin_hot<false>, and reports whether both rail decisions are provably the
@@ -103,10 +112,13 @@ constexpr float kEvmGuard = 512.f;
 // here, so the test is done on G (numerator, thresholds and guards scaled accordingly, rH2 = 2 rH) and the quotient
 // is recovered with k = 4 sc = 1 / sc ... E = F conj(G) / |G|^2 * k; the sign of sc joins the sign comparison.
 __device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 G, float k, uint32_t txp, float rF, float rH2, float den_min4,
-                                                        float &e2, bool &doubt)
+                                                        float2 &e2, bool &doubt)
 {
     const float a = F.x, b = F.y, c = G.x, d = G.y;
-    const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
+    // numerator F * conj(G) = (fma(a, c, b*d), fma(b, c, -(a*d))) in two packed instructions
+    const float2 pt = __fmul2_rn(make_float2(d, d), make_float2(b, a));
+    const float2 S = __ffma2_rn(make_float2(c, c), F, make_float2(pt.x, -pt.y));
+    const float sr = S.x, si = S.y;
     const float den = fmaf(c, c, d * d);
     float inv;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
@@ -118,8 +130,10 @@ __device__ __forceinline__ uint32_t process_bin_checked(float2 F, float2 G, floa
     // reference numerator >= 1e-30 in magnitude and reference |H|^2 < 1e14: the float quotient keeps its sign (>= 1e-44)
     const bool safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 2e-30f && den < 1.6e14f && den > den_min4;
     doubt = doubt || !safe;
-    const float er = fmaf(sr * inv, k, -__uint_as_float(0x3F3504F3u | sx)), eim = fmaf(si * inv, k, -__uint_as_float(0x3F3504F3u | sq));
-    e2 += fmaf(er, er, eim * eim);
+    // E - tx = (S * inv) * k - (+-1/sqrt(2)); e2 collects the squares of the two rails separately (summed per frame)
+    const float2 U = __fmul2_rn(S, make_float2(inv, inv));
+    const float2 D = __ffma2_rn(U, make_float2(k, k), make_float2(__uint_as_float(0xBF3504F3u ^ sx), __uint_as_float(0xBF3504F3u ^ sq)));
+    e2 = __ffma2_rn(D, D, e2);
     return ei_ | (eq_ << 8) | ((ei_ & eq_) << 16);
 }
 
@@ -131,6 +145,7 @@ struct McParams {
     float snr_lin[kMaxSnr];         // (float)pow(10, snr/10), OFDM.c:645
     float inv_sqrt_snr[kMaxSnr];    // 1/sqrt(snr_lin), fast mode's noise scale factor
     float radius_scale;             // kArithChecked: kRadius, or infinity to replay every point
+    float radius_chan;              // kArithChecked: kChanRadius * sqrt(320) (times sqrt(P) = the channel term), or infinity
     int n_taps;                     // multipath variant: taps per frame (1..kMaxTaps)
     ofdm_counters *counters;        // [n_snr], accumulated into
 };
@@ -358,13 +373,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
             philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)blk_base, kDomainNoise, za);
             philox_normals4(p.seed, (uint32_t)si, fr, (uint32_t)(blk_base + 8), kDomainNoise, zb);
             float2 r[8];
-            float n2 = 0.f;                                       // CHECKED: the lane's share of the window's energy
+            float2 n2 = make_float2(0.f, 0.f);                    // CHECKED: the lane's share of the window's energy (re^2, im^2)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int m = slot_m<EXACT>(i);
                 float2 s = src[u + 8 * m];
                 const float z = m < 4 ? za[m & 3] : zb[m & 3];
-                if (CHECKED) { s.x = add_noise<true>(s.x, z, sigma_d, sigma_f); n2 = fmaf(s.x, s.x, fmaf(s.y, s.y, n2)); }
+                if (CHECKED) { s.x = fmaf(sigma_f, z, s.x); n2 = __ffma2_rn(s, s, n2); }      // speculated channel (see kChanRadius)
                 else s.x = add_noise_s<EXACT>(s.x, z, sigma_d, sigma_f);
                 r[i] = s;
             }
@@ -374,11 +389,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[u + 8 * j] = r[j];
             float rad = 0.f;
-            if (CHECKED) rad = window_radius(n2, p.radius_scale);
+            if (CHECKED) rad = window_radius(n2, p.radius_scale, p.radius_chan * sqrtP);
             __syncwarp();
             float e2 = 0.f;
             uint32_t pk = 0;
             if (CHECKED) {
+                float2 e2v = make_float2(0.f, 0.f);
                 const float rA = __shfl_sync(0xffffffffu, rad, 0), rB = __shfl_sync(0xffffffffu, rad, 8);
                 const float r0 = __shfl_sync(0xffffffffu, rad, 16), r1 = __shfl_sync(0xffffffffu, rad, 24);
                 const float rH2 = rA + rB;                                        // 2 r_H
@@ -387,10 +403,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
-                    const float2 G = make_float2(A.x + B.x, A.y + B.y);
+                    const float2 G = cadd(A, B);
                     const float rF = t == 0 ? r0 : t == 2 ? r1 : (lane < 16 ? r0 : r1);
-                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], txp[t], rF, rH2, den_min4, e2, doubt);
+                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], txp[t], rF, rH2, den_min4, e2v, doubt);
                 }
+                e2 = e2v.x + e2v.y;
                 __syncwarp();
                 if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
                     const uint32_t txp3 = (txp[0] & 3u) | ((txp[1] & 3u) << 2) | ((txp[2] & 3u) << 4);
@@ -601,7 +618,6 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
 {
     constexpr bool EXACT = ARITH == kArithExact;                // transform / decision arithmetic of the main path
     constexpr bool CHECKED = ARITH == kArithChecked;
-    constexpr bool EXACT_CHANNEL = EXACT || CHECKED;
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
     __shared__ double s_sum[kWarpsPerBlock][2];
@@ -689,14 +705,14 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
             }
             tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
             float2 v[8];
-            float n2 = 0.f;                                       // CHECKED: the lane's share of the window's energy
+            float2 n2 = make_float2(0.f, 0.f);                    // CHECKED: the lane's share of the window's energy (re^2, im^2)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int m = slot_m<EXACT>(i);
                 float2 smp = ws.st[s].x[grp][u + 8 * m];
-                if (NOISE == kNoiseInject) smp.x = add_noise<EXACT_CHANNEL>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
-                if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT_CHANNEL>(smp.x, z[m], sigma_d, sigma_f);
-                if (CHECKED) n2 = fmaf(smp.x, smp.x, fmaf(smp.y, smp.y, n2));
+                if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);   // CHECKED: speculated (kChanRadius)
+                if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
+                if (CHECKED) n2 = __ffma2_rn(smp, smp, n2);
                 v[i] = smp;
             }
             __syncwarp();                                         // every lane has its samples: the stage can be refilled
@@ -706,13 +722,14 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[u + 8 * j] = v[j];
             if (CHECKED) {
-                const float r = window_radius(n2, p.radius_scale);
+                const float r = window_radius(n2, p.radius_scale, NOISE != kNoiseNone ? p.radius_chan * sigma_f : 0.f);
                 if (u == 0) ws.radius[grp] = r;
             }
             __syncwarp();
             float f_e2 = 0.f;
             uint32_t pk = 0;
             if (CHECKED) {
+                float2 e2v = make_float2(0.f, 0.f);
                 const float4 rad = *reinterpret_cast<const float4 *>(ws.radius);
                 const float rH2 = rad.x + rad.y;                                  // 2 r_H
                 const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
@@ -720,12 +737,13 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
-                    const float2 G = make_float2(A.x + B.x, A.y + B.y);
+                    const float2 G = cadd(A, B);
                     const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
                     // items 0..31 belong to symbol 0, 64..95 to symbol 1, 32..63 split at lane 16
                     const float rF = t == 0 ? rad.z : t == 2 ? rad.w : (lane < 16 ? rad.z : rad.w);
-                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], w >> ic.shift[t], rF, rH2, den_min4, f_e2, doubt);
+                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], w >> ic.shift[t], rF, rH2, den_min4, e2v, doubt);
                 }
+                f_e2 = e2v.x + e2v.y;
                 __syncwarp();
                 if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
                     const uint2 r = stream_frame_replay<NOISE>(p.in + f * len, NOISE == kNoiseInject ? p.g + f * len : nullptr,
@@ -875,7 +893,7 @@ __device__ __noinline__ SweepTotals sweep_frame_replay(SweepFrame fr, float2 *ti
 template <int ARITH, int NOISE>
 __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
 {
-    constexpr bool EXACT = ARITH == kArithExact, CHECKED = ARITH == kArithChecked, EXACT_CHANNEL = EXACT || CHECKED;
+    constexpr bool EXACT = ARITH == kArithExact, CHECKED = ARITH == kArithChecked;
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
     __shared__ double s_sum[kWarpsPerBlock][2];
@@ -990,24 +1008,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                 }
                 tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
                 float2 v[8];
-                float n2 = 0.f;
+                float2 n2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int m = slot_m<EXACT>(i);
                     float2 smp = make_float2(0.f, 0.f);
                     if (active) {
                         smp = ws.st[s].x[grp][u + 8 * m];
-                        if (NOISE == kNoiseInject) smp.x = add_noise<EXACT_CHANNEL>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);
-                        if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT_CHANNEL>(smp.x, z[m], sigma_d, sigma_f);
+                        if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);   // CHECKED: speculated
+                        if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
                     }
-                    if (CHECKED) n2 = fmaf(smp.x, smp.x, fmaf(smp.y, smp.y, n2));
+                    if (CHECKED) n2 = __ffma2_rn(smp, smp, n2);
                     v[i] = smp;
                 }
                 __syncwarp();                                     // every lane has its samples: the stage can be refilled
                 issue_next(s);
                 fft64<EXACT>(v, tw, tile, u);
                 float rad = 0.f;
-                if (CHECKED) rad = window_radius(n2, p.radius_scale);
+                if (CHECKED) rad = window_radius(n2, p.radius_scale, NOISE != kNoiseNone ? p.radius_chan * sigma_f : 0.f);
                 uint32_t pk = 0;
                 if (pass == 0) {
                     float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
@@ -1031,8 +1049,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                         uint32_t r;
                         if (CHECKED) {
                             bool dbt = false;
-                            r = process_bin_checked(ws.tile[ic.f_off[t]], make_float2(A.x + B.x, A.y + B.y), 4.f * ic.sc[t], w >> ic.shift[t],
-                                                    isym == 0 ? r4.z : r4.w, rH2, den_min4, e2, dbt);
+                            float2 e2v = make_float2(0.f, 0.f);
+                            r = process_bin_checked(ws.tile[ic.f_off[t]], cadd(A, B), 4.f * ic.sc[t], w >> ic.shift[t],
+                                                    isym == 0 ? r4.z : r4.w, rH2, den_min4, e2v, dbt);
+                            e2 = e2v.x + e2v.y;
                             doubt = doubt || (valid && dbt);
                         } else {
                             const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848
@@ -1064,8 +1084,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                             uint32_t r;
                             if (CHECKED) {
                                 bool dbt = false;
+                                float2 e2v = make_float2(0.f, 0.f);
                                 const float rF = round == 0 ? (isym == 0 ? r4.x : r4.y) : (isym == 0 ? r4.z : r4.w);
-                                r = process_bin_checked(F, make_float2(A.x + B.x, A.y + B.y), 4.f * ic.sc[t], w >> ic.shift[t], rF, rH2, den_min4, e2, dbt);
+                                r = process_bin_checked(F, cadd(A, B), 4.f * ic.sc[t], w >> ic.shift[t], rF, rH2, den_min4, e2v, dbt);
+                                e2 = e2v.x + e2v.y;
                                 doubt = doubt || (valid && dbt);
                             } else {
                                 const float2 Hh = make_float2(__fmul_rn(__fadd_rn(A.x, B.x), ic.sc[t]), __fmul_rn(__fadd_rn(A.y, B.y), ic.sc[t]));   // :848

@@ -46,17 +46,34 @@ __constant__ Tables c_tab;
 
 __device__ __forceinline__ int rev3(int v) { return ((v & 1) << 2) | (v & 2) | ((v >> 2) & 1); }
 
+// ---------------------------------------------------------------- packed fp32 (sm_100 FADD2 / FMUL2 / FFMA2)
+// A complex value is a float2 = one 64-bit register pair, and Blackwell's packed fp32 instructions operate on such
+// pairs lane by lane with round-to-nearest per lane: one issue slot per complex add instead of two.  Their operands
+// take a swap (LO_HI), per-lane negation and a scalar broadcast for free, so a rotation by -i, a conjugate or
+// "real part times complex" cost nothing extra: ptxas folds the make_float2() shuffles below into operand modifiers
+// (profiles/r2_sass_*.txt: no MOV / PRMT around them).  Every helper is bit-identical to the scalar expression in
+// its comment.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }   // a + b*(-i)
+__device__ __forceinline__ float2 csub_mi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }   // a - b*(-i)
+// (fma(a.x, b.x, -(a.y*b.y)), fma(a.x, b.y, a.y*b.x)): FMUL2 with a broadcast, FFMA2 with a mixed-sign addend
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x));
+    return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-t.x, t.y));
+}
+
 // ---------------------------------------------------------------- exact-mode butterflies
 // W * o with W double, o float promoted: (wr*c - wi*d) + i(wr*d + wi*c), each op rounded
 // separately (gcc without -mfma), then rounded to float; e +- that in float.  OFDM.c:303-305
 __device__ __forceinline__ void bf_exact(float2 &e, float2 &o, double wr, double wi)
 {
     double c = (double)o.x, d = (double)o.y;
-    float wx = __double2float_rn(__dsub_rn(__dmul_rn(wr, c), __dmul_rn(wi, d)));
-    float wy = __double2float_rn(__dadd_rn(__dmul_rn(wr, d), __dmul_rn(wi, c)));
-    float2 a = e;
-    e.x = __fadd_rn(a.x, wx); e.y = __fadd_rn(a.y, wy);
-    o.x = __fsub_rn(a.x, wx); o.y = __fsub_rn(a.y, wy);
+    const float2 w = make_float2(__double2float_rn(__dsub_rn(__dmul_rn(wr, c), __dmul_rn(wi, d))),
+                                 __double2float_rn(__dadd_rn(__dmul_rn(wr, d), __dmul_rn(wi, c))));
+    const float2 a = e;
+    e = cadd(a, w); o = csub(a, w);
 }
 // float -> double without the XU pipe.  The float's bits are re-laid as a double with the SAME biased exponent
 // field, i.e. the value x * 2^-896 (exact for normals, denormals and zeros: a zero exponent field means
@@ -74,18 +91,16 @@ __device__ __forceinline__ double f2d_scaled(float x)
 __device__ __forceinline__ void bf_exact_s(float2 &e, float2 &o, double wr, double wi)
 {
     const double c = f2d_scaled(o.x), d = f2d_scaled(o.y);
-    float wx = __double2float_rn(__dsub_rn(__dmul_rn(wr, c), __dmul_rn(wi, d)));
-    float wy = __double2float_rn(__dadd_rn(__dmul_rn(wr, d), __dmul_rn(wi, c)));
-    float2 a = e;
-    e.x = __fadd_rn(a.x, wx); e.y = __fadd_rn(a.y, wy);
-    o.x = __fsub_rn(a.x, wx); o.y = __fsub_rn(a.y, wy);
+    const float2 w = make_float2(__double2float_rn(__dsub_rn(__dmul_rn(wr, c), __dmul_rn(wi, d))),
+                                 __double2float_rn(__dadd_rn(__dmul_rn(wr, d), __dmul_rn(wi, c))));
+    const float2 a = e;
+    e = cadd(a, w); o = csub(a, w);
 }
 // k = 0: W = (1, -0); the product equals o for every finite o (up to the sign of a zero)
 __device__ __forceinline__ void bf_unit(float2 &e, float2 &o)
 {
-    float2 a = e, w = o;
-    e.x = __fadd_rn(a.x, w.x); e.y = __fadd_rn(a.y, w.y);
-    o.x = __fsub_rn(a.x, w.x); o.y = __fsub_rn(a.y, w.y);
+    const float2 a = e, w = o;
+    e = cadd(a, w); o = csub(a, w);
 }
 
 // k = sz/4: W = (6.1e-17, -1) exactly as cexp() returns it.  The product is
@@ -96,9 +111,8 @@ __device__ __forceinline__ void bf_quarter(float2 &e, float2 &o)
 {
     const float c = o.x, d = o.y;
     if (fabsf(c) * 1e-8f < fabsf(d) && fabsf(d) * 1e-8f < fabsf(c)) {
-        float2 a = e;
-        e.x = __fadd_rn(a.x, d); e.y = __fsub_rn(a.y, c);
-        o.x = __fsub_rn(a.x, d); o.y = __fadd_rn(a.y, c);
+        const float2 a = e, w = o;
+        e = cadd_mi(a, w); o = csub_mi(a, w);           // a +- (d, -c)
     } else {
         bf_exact(e, o, kW16r, kW16i);
     }
@@ -153,29 +167,21 @@ __device__ __forceinline__ void fft64_exact(float2 (&v)[8], const TwExact &tw, f
 }
 
 // ---------------------------------------------------------------- fast-mode fp32 transform
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
-{
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
-
-// forward 8-point DFT, natural order in and out (decimation in frequency)
+// forward 8-point DFT, natural order in and out (decimation in frequency); 28 packed instructions
 __device__ __forceinline__ void dft8(float2 (&v)[8])
 {
     const float h = 0.70710678118654752440f;
-    float2 a0 = cadd(v[0], v[4]), b0 = csub(v[0], v[4]);
-    float2 a1 = cadd(v[1], v[5]), b1 = csub(v[1], v[5]);
-    float2 a2 = cadd(v[2], v[6]), b2 = csub(v[2], v[6]);
-    float2 a3 = cadd(v[3], v[7]), b3 = csub(v[3], v[7]);
-    b1 = make_float2((b1.x + b1.y) * h, (b1.y - b1.x) * h);      // * W8^1
-    b2 = mul_mi(b2);                                             // * W8^2
-    b3 = make_float2((b3.y - b3.x) * h, -(b3.x + b3.y) * h);     // * W8^3
-    float2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), s3 = mul_mi(csub(a1, a3));
-    v[0] = cadd(s0, s2); v[4] = csub(s0, s2); v[2] = cadd(s1, s3); v[6] = csub(s1, s3);
-    float2 t0 = cadd(b0, b2), t1 = csub(b0, b2), t2 = cadd(b1, b3), t3 = mul_mi(csub(b1, b3));
-    v[1] = cadd(t0, t2); v[5] = csub(t0, t2); v[3] = cadd(t1, t3); v[7] = csub(t1, t3);
+    const float2 hh = make_float2(h, h);
+    const float2 a0 = cadd(v[0], v[4]), b0 = csub(v[0], v[4]);
+    const float2 a1 = cadd(v[1], v[5]), b1d = csub(v[1], v[5]);
+    const float2 a2 = cadd(v[2], v[6]), b2 = csub(v[2], v[6]);          // b2 * W8^2 = b2 * (-i): folded into its consumers
+    const float2 a3 = cadd(v[3], v[7]), b3d = csub(v[3], v[7]);
+    const float2 b1 = __fmul2_rn(cadd_mi(b1d, b1d), hh);                                                         // * W8^1: ((x+y)h, (y-x)h)
+    const float2 b3 = __fmul2_rn(__fadd2_rn(make_float2(b3d.y, -b3d.x), make_float2(-b3d.x, -b3d.y)), hh);       // * W8^3: ((y-x)h, -(x+y)h)
+    const float2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), d3 = csub(a1, a3);
+    v[0] = cadd(s0, s2); v[4] = csub(s0, s2); v[2] = cadd_mi(s1, d3); v[6] = csub_mi(s1, d3);
+    const float2 t0 = cadd_mi(b0, b2), t1 = csub_mi(b0, b2), t2 = cadd(b1, b3), e3 = csub(b1, b3);
+    v[1] = cadd(t0, t2); v[5] = csub(t0, t2); v[3] = cadd_mi(t1, e3); v[7] = csub_mi(t1, e3);
 }
 
 struct TwFast { float2 w[7]; };    // W_64^(u*k), k = 1..7

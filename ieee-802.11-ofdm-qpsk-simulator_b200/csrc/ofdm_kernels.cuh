@@ -316,6 +316,7 @@ struct RxParams {
     int n_sym;
     float snr_lin;
     float radius_scale;         // kArithChecked: error-radius factor (kRadius; infinity forces every frame to be replayed)
+    float radius_chan;          // kArithChecked: kChanRadius * sqrt(frame_len * snr_lin): times sigma = the speculated channel's share
     uint32_t seed, stream;
     uint64_t frame0;
     ofdm_counters *counters;
@@ -378,11 +379,14 @@ template <bool EXACT>
 __device__ __forceinline__ uint32_t process_bin_hot(float2 F, float2 Hh, float sc, uint32_t txp, bool valid, float &e2)
 {
     const float a = F.x, b = F.y, c = Hh.x, d = Hh.y;
-    const float sr = fmaf(a, c, b * d), si = fmaf(b, c, -(a * d));
+    // numerator F * conj(H) = (fma(a, c, b*d), fma(b, c, -(a*d))): FMUL2 with a broadcast + FFMA2 with a mixed-sign addend
+    const float2 pt = __fmul2_rn(make_float2(d, d), make_float2(b, a));
+    const float2 S = __ffma2_rn(make_float2(c, c), F, make_float2(pt.x, -pt.y));
+    const float sr = S.x, si = S.y;
     const float den = fmaf(c, c, d * d);
     float inv;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
-    float ex = sr * inv, ey = si * inv;
+    float2 E = __fmul2_rn(S, make_float2(inv, inv));
     const uint32_t sq = txp << 31, sx = (txp ^ (txp >> 1)) << 31;          // IEEE sign bits of the tx Q / I rails
     uint32_t ei_ = (__float_as_uint(sr) ^ sx) >> 31, eq_ = (__float_as_uint(si) ^ sq) >> 31;
     if (EXACT) {
@@ -391,14 +395,14 @@ __device__ __forceinline__ uint32_t process_bin_hot(float2 F, float2 Hh, float s
         const float m = (fabsf(a) + fabsf(b)) * (fabsf(c) + fabsf(d));
         const bool safe = fminf(fabsf(sr), fabsf(si)) > fmaxf(1e-6f * m, 1e-30f) && den < 1e14f;
         if (!safe && valid) {
-            const float2 E = div_exact(F, Hh, sc);
-            ex = E.x; ey = E.y;
+            E = div_exact(F, Hh, sc);
             ei_ = (uint32_t)((E.x > 0.f) != (sx == 0u));
             eq_ = (uint32_t)((E.y > 0.f) != (sq == 0u));
         }
     }
-    const float er = ex - __uint_as_float(0x3F3504F3u | sx), eim = ey - __uint_as_float(0x3F3504F3u | sq);
-    const float t = fmaf(er, er, eim * eim);
+    // E - tx point: the tx rails are +-1/sqrt(2) = 0x3F3504F3 with the sign bits above
+    const float2 D = __fadd2_rn(E, make_float2(__uint_as_float(0xBF3504F3u ^ sx), __uint_as_float(0xBF3504F3u ^ sq)));
+    const float t = fmaf(D.x, D.x, D.y * D.y);
     e2 += valid ? t : 0.f;
     const uint32_t pk = ei_ | (eq_ << 8) | ((ei_ & eq_) << 16);
     return valid ? pk : 0u;

@@ -321,6 +321,28 @@ void orc_chain(const uint8_t *bits, const float *g, long n_frames, int n_sym, fl
     free(tx); free(ota); free(mod);
 }
 
+/* sweep form: transmitter once per frame, channel + receiver per SNR point (main() :1191-1222); acc[n_snr] */
+void orc_chain_sweep(const uint8_t *bits, const float *g, long n_frames, int n_sym, const float *snr_db, int n_snr,
+                     int noise_mode, orc_counters *acc)
+{
+    orc_init();
+    int len = 160 + 80 * n_sym;
+    cf32 *tx = (cf32 *)malloc(sizeof(cf32) * (size_t)len), *ota = (cf32 *)malloc(sizeof(cf32) * (size_t)len);
+    cf32 *mod = (cf32 *)malloc(sizeof(cf32) * 48 * (size_t)n_sym);
+    for (long f = 0; f < n_frames; ++f) {
+        const uint8_t *b = bits + f * 96 * n_sym;
+        tx_frame(b, n_sym, tx, mod);
+        for (int s = 0; s < n_snr; ++s) {
+            if (noise_mode == 0) awgn_inject(tx, g + f * len, ota, snr_db[s], len);
+            else memcpy(ota, tx, sizeof(cf32) * (size_t)len);
+            orc_rx_stats st;
+            rx_frame(ota, n_sym, b, mod, NULL, NULL, NULL, NULL, &st);
+            accumulate(acc + s, &st, n_sym);
+        }
+    }
+    free(tx); free(ota); free(mod);
+}
+
 /* ---------------- counter-based streams (new-build definition, mirrored by csrc/philox.cuh) ---------------- */
 
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])

@@ -42,6 +42,9 @@ void  orc_rx_frame(const float *ota, int n_sym, const uint8_t *tx_bits, float *H
 void  orc_chain(const uint8_t *bits, const float *g, long n_frames, int n_sym, float snr_db, int noise_mode,
                 orc_counters *acc, int *frame_bit_errors, float *frame_evm_lin);
 
+void  orc_chain_sweep(const uint8_t *bits, const float *g, long n_frames, int n_sym, const float *snr_db, int n_snr,
+                      int noise_mode, orc_counters *acc /* [n_snr] */);
+
 /* Counter-based streams shared with the CUDA Monte-Carlo kernels (new-build definition,
  * see DESIGN.md "Philox streams"): Philox4x32-10, key = (seed, stream),
  * counter = (frame_lo, frame_hi, block, domain). */

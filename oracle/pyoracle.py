@@ -207,6 +207,19 @@ class _Base:
                          C.byref(acc), _p(fe, C.c_int) if per_frame else None, _p(fv) if per_frame else None)
         return (acc, fe, fv) if per_frame else acc
 
+    def chain_sweep(self, bits, g, n_sym, snr_db, noise_mode=0):
+        """Transmitter once per frame, channel + receiver per SNR point (the loop of main() :1191-1222); list of Counters."""
+        bits = _u8(bits).reshape(-1, 96 * n_sym)
+        n = bits.shape[0]
+        gp = None
+        if noise_mode == 0:
+            g = _f32(g).reshape(n, self.frame_len(n_sym))
+            gp = _p(g)
+        snr = np.ascontiguousarray(snr_db, dtype=np.float32)
+        acc = (Counters * len(snr))()
+        self._f("chain_sweep")(_p(bits, C.c_uint8), gp, C.c_long(n), C.c_int(n_sym), _p(snr), C.c_int(len(snr)), C.c_int(noise_mode), acc)
+        return list(acc)
+
 
 class Ref(_Base):
     """The compiled, unmodified reference (oracle/_ref)."""

@@ -371,6 +371,40 @@ void ref_chain(const uint8_t *bits, const float *g, long n_frames, int n_sym, fl
     Deallocate_Array_2D(mod, n_sym);
 }
 
+/* The same as main() :1191-1222 arranges it: Transmitter once per frame, then channel + receiver per SNR point
+ * (ref_chain above re-runs the transmitter for every SNR point; this is the fair CPU arm for a sweep).
+ * acc[n_snr]; noise_mode as in ref_chain, the injected draws are reused across SNR points (only the scale changes). */
+void ref_chain_sweep(const uint8_t *bits, const float *g, long n_frames, int n_sym, const float *snr_db, int n_snr,
+                     int noise_mode, ref_counters *acc)
+{
+    int len = 160 + 80*n_sym;
+    float complex *tx = Allocate_Array_1D(len), *ota = Allocate_Array_1D(len);
+    float complex **mod = Allocate_Array_2D(n_sym, 48);
+    for (long f = 0; f < n_frames; ++f) {
+        const uint8_t *b = bits + f * 96 * n_sym;
+        tx_frame_c(b, n_sym, tx, mod);
+        for (int s = 0; s < n_snr; ++s) {
+            if (noise_mode == 0)      awgn_inject_c(tx, g + f * len, ota, snr_db[s], len);
+            else if (noise_mode == 1) Transmission_Over_Air(tx, ota, snr_db[s], len);
+            else                      memcpy(ota, tx, len * sizeof(float complex));
+            ref_rx_stats st;
+            rx_frame_c(ota, n_sym, b, mod, NULL, NULL, NULL, NULL, &st);
+            ref_counters *a = acc + s;
+            a->bit_errors += st.bit_errors;
+            a->bits += 96 * n_sym;
+            a->frames_in_error += st.bit_errors > 0;
+            a->rail_errors += st.rail_errors;
+            a->frames += 1;
+            double e = (double)st.evm_lin;
+            a->sum_evm_lin += e;
+            a->sum_err2 += e * e * 48.0 * n_sym;
+            a->sum_ref2 += 48.0 * n_sym;
+        }
+    }
+    free(tx); free(ota);
+    Deallocate_Array_2D(mod, n_sym);
+}
+
 /* cfg0: the reference's own main() :1187, seeded through the time() shim; it writes
  * data/Output_*.txt relative to the cwd, so the caller chdir()s first. */
 int ref_main_default(unsigned seed, int quiet)

@@ -77,3 +77,19 @@ def test_streaming_16mi_symbols(ofdm, pkg):
     frames = ofdm.tx_frames(bits, NSYM, pkg.MODE_FAST, with_power=False)
     cnt, _ = ofdm.rx_frames(frames, bits, NSYM, pkg.MODE_FAST)
     assert cnt.frames == n and cnt.bits == n * 192 and cnt.bit_errors == 0
+
+
+def test_cfg1_against_the_compiled_reference_100k(pkg, lib, ref):
+    """configs[1] against the reference itself at 100,000 frames x 21 SNR points: draws from the reference's own
+    rand() / Box-Muller stream, oracle/_ref's ref_chain_sweep on all host cores vs ofdm_sweep_inject_host in EXACT
+    mode -- every integer total equal at every point, EVM sums within 1e-5.  (tools/full_parity.py runs the same at
+    the full 1,000,000 frames; its output is kept under profiles/.)"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import full_parity
+    res = full_parity.run(100_000, len(os.sched_getaffinity(0)), verbose=False)
+    bad = [p for p in res["points"] if not p["ints_equal"] or p["evm_rel_diff"] > 1e-5 or p["evm_lin_sum_rel_diff"] > 1e-5]
+    assert res["pass"] and not bad, bad
+    assert res["points"][0]["gpu"][1] == 100_000 * 192 and res["points"][0]["gpu"][4] == 100_000
