@@ -3,20 +3,29 @@
 
 Workload (configs[1]): batched QPSK BER/EVM sweep, 1,000,000 frames x 2 data symbols, 21 SNR points
 0..20 dB, injected standard-normal draws (one per sample, reused across SNR points), EXACT mode
-(bit-exact error counts versus OFDM.c).  One "step" = one whole sweep: Transmitter once, then per SNR
-point the fused channel+receiver kernel.  A counted OFDM symbol is one data symbol that went through
-TX, the channel and RX at one SNR point: symbols/step = frames x n_sym x n_snr.
+(bit-exact error counts versus OFDM.c).  One "step" = one whole sweep: Transmitter once, then channel +
+receiver at every SNR point.  A counted OFDM symbol is one data symbol that went through TX, the channel and
+RX at one SNR point: symbols/step = frames x n_sym x n_snr.
 
-  value   inputs resident in HBM, CUDA-event timed on the launching stream
+  value   inputs resident in HBM, CUDA-event timed on the launching stream.  The SNR loop runs in ONE kernel
+          (k_sweep_lin: FFT(x + sigma g) = FFT(x) + sigma FFT(g), so each frame and its draws are transformed once
+          and every SNR point costs a multiply-add per bin plus the verified decision stage).
   e2e     the same sweep through ofdm_sweep_inject_host: HOST (pinned) bits + draws, H2D copies,
           kernels and the D2H of the counters inside the timed region
-  roofline  dominant kernel k_stream_rx2<checked,inject> (EXACT mode: fp32 speculation, verified, doubtful
-            frames replayed in the reference's arithmetic): algorithmic bytes (3100 B per frame and SNR
-            point) / mean launch time (CUDA events around each launch in the timed region)
+  roofline  the HBM-bound kernel of the path: k_stream_rx2<checked,inject>, the fused channel + receiver of ONE SNR
+            point (what the stage API ofdm_awgn_rx_inject launches, and what the sweep launched 21 times before
+            k_sweep_lin existed): algorithmic bytes (3100 B per frame) / mean launch time, CUDA events
+            around each launch of a dedicated loop of steps x 21 launches in this run.  sweep_kernel describes
+            k_sweep_lin, which is bound by instruction issue, not by HBM.
+  configs   configs[2] (streaming TX / RX of 16 Mi HBM-resident symbols, HBM GB/s fraction), configs[3] (fused on-chip
+            Philox Monte-Carlo, fixed frame count and the until-100-errors-or-1e-7-budget rule), configs[4] (8-tap
+            multipath): per-config throughput and roofline; at N > 1 configs[3] / [4] are sharded by global frame index
+            with the NCCL all-reduce of the counters inside the timed region (time = max over ranks).
   cpu_baseline  the compiled reference (oracle/_ref) stage chain on a bounded sample, one thread
 
 --impl reference: the reference's own CPU implementation of the path (oracle/_ref, else the oracle
-port) on all host cores, each step a bounded sample of the same workload.
+port) on all host cores, each step a bounded sample of the same workload (Transmitter once per frame, then
+channel + receiver per SNR point, as main() arranges it).
 Multi-GPU (torchrun): frames are sharded across ranks (weak scaling: 1M frames per rank), one NCCL
 all-reduce of the counters per sweep; time = max over ranks.
 """
@@ -105,10 +114,7 @@ def _worker_init():
 def _worker_run(args):
     bits, g, snrs = args
     impl = _W["impl"]
-    tot = 0
-    for s in snrs:
-        tot += impl.chain(bits, g, N_SYM, s).bit_errors
-    return tot
+    return sum(c.bit_errors for c in impl.chain_sweep(bits, g, N_SYM, snrs))
 
 
 def sample_inputs(n_frames, seed):
@@ -142,8 +148,7 @@ def cpu_baseline_single(sample_frames):
     bits, g = sample_inputs(sample_frames, 1234)
     impl.chain(bits[:64], g[:64], N_SYM, 10.0)          # warm
     t0 = time.perf_counter()
-    for s in SNRS:
-        impl.chain(bits, g, N_SYM, s)
+    impl.chain_sweep(bits, g, N_SYM, SNRS)              # Transmitter once per frame, 21 x (channel + receiver): main()'s loop
     dt = time.perf_counter() - t0
     return {"value": sample_frames * N_SYM * len(SNRS) / dt, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": "%d frames x %d symbols x %d SNR points, injected normals, %.1f s" % (sample_frames, N_SYM, len(SNRS), dt),
@@ -348,6 +353,104 @@ def bind_near_gpu(local):
         return "unavailable (%s)" % type(e).__name__
 
 
+def kernel_metrics():
+    """ncu-derived pipe / issue utilisation of the kernels that are not HBM-bound (profiles/r2_kernel_metrics.json, written by
+    tools/ncu_summary.py from the committed ncu captures); None when the file is absent"""
+    path = os.path.join(ROOT, "profiles", "r2_kernel_metrics.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def run_configs(o, pkg, torch, dist, dev, args, rank, world):
+    """configs[2], [3], [4] of BASELINE.json, each with its own roofline statement.  Returns the dict on every rank
+    (aggregates are over all ranks: time = max over ranks, work = sum)."""
+    peak, _ = peaks()
+    km = kernel_metrics()
+    lib, h = o.lib, o.h
+    out = {}
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- configs[2]: streaming TX + RX of HBM-resident frames (16 Mi data symbols per GPU), HBM-bound
+    n = args.stream_frames
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n * N_SYM * 3,), dtype=torch.int32, device=dev)
+    frames = torch.empty((n, pkg.frame_len(N_SYM), 2), dtype=torch.float32, device=dev)
+    cnt = o.new_counters(1)
+    tx_bytes, rx_bytes = n * (24 + 2560), n * (2048 + 24)
+    c2 = {"frames_per_gpu": n, "data_symbols_per_gpu": n * N_SYM, "bytes_per_frame": {"tx": 24 + 2560, "rx": 2048 + 24},
+          "note": "rx reads only the LTS halves and the symbol bodies (2048 B of the 2560 B frame) + 24 B of bits; inputs larger than L2"}
+    for mode, name in ((pkg.MODE_FAST, "fast"), (pkg.MODE_EXACT, "exact")):
+        ms_tx = timed(lambda: o._check(lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), None, n, N_SYM, mode)), 5)
+        cnt.zero_()
+        ms_rx = timed(lambda: o._check(lib.ofdm_rx_frames(h, frames.data_ptr(), bits.data_ptr(), n, N_SYM, mode, cnt.data_ptr(), None)), 5)
+        assert int(o.read_counters(cnt)[0].bit_errors) == 0            # noise-free round trip
+        c2[name] = {"tx": {"ms": ms_tx, "roofline": {"bound": "hbm", "achieved": tx_bytes / ms_tx / 1e6, "peak": peak, "unit": "GB/s",
+                                                      "frac": tx_bytes / ms_tx / 1e6 / peak}},
+                    "rx": {"ms": ms_rx, "roofline": {"bound": "hbm", "achieved": rx_bytes / ms_rx / 1e6, "peak": peak, "unit": "GB/s",
+                                                      "frac": rx_bytes / ms_rx / 1e6 / peak}},
+                    "symbols_per_s_tx_plus_rx": world * n * N_SYM / ((ms_tx + ms_rx) * 1e-3)}
+    out["cfg2_streaming"] = c2
+    del frames, bits
+    torch.cuda.empty_cache()
+
+    # ---- configs[3] / configs[4]: on-chip Philox Monte-Carlo, sharded by global frame index, all-reduce inside the timed region
+    nm = args.mc_frames
+    mc = o.new_counters(len(SNRS))
+
+    def mc_step(mode, n_taps):
+        mc.zero_()
+        o.mc_sweep_points(7, rank * nm, nm, N_SYM, n_taps, SNRS, None, mode, mc)
+        if world > 1:
+            pkg.sweep.allreduce_counter_tensor(mc)
+
+    for key, n_taps in (("cfg3_philox_mc", 0), ("cfg4_multipath_8taps", 8)):
+        c = {"frames_per_gpu": nm, "snr_points": len(SNRS), "taps": n_taps,
+             "parallelism": "global frame index sharded over %d GPU(s), one NCCL all-reduce of the counters per sweep (inside the timed region)" % world}
+        for mode, name in ((pkg.MODE_FAST, "fast"), (pkg.MODE_EXACT, "exact")):
+            ms = timed(lambda: mc_step(mode, n_taps), 2)
+            tot = o.read_counters(mc)
+            assert all(t.frames == world * nm and t.bits == world * nm * 96 * N_SYM for t in tot), "all-reduced totals"
+            sym = world * nm * N_SYM * len(SNRS) / (ms * 1e-3)
+            c[name] = {"ms": ms, "symbols_per_s": sym, "symbols_per_s_per_gpu": sym / world,
+                       "fft_tflops_per_gpu": nm * len(SNRS) * 4 * 1920 / (ms * 1e-3) / 1e12,
+                       "ber_0_10_14dB": [tot[0].bit_errors / tot[0].bits, tot[10].bit_errors / tot[10].bits, tot[14].bit_errors / tot[14].bits],
+                       "roofline": dict({"bound": "issue (on-chip: no HBM traffic beyond the counters)"},
+                                        **km.get("k_mc_philox_%s%s" % (name, "_multipath" if n_taps else ""), {}))}
+        out[key] = c
+
+    # ---- configs[3] as stated: every SNR point until >= 100 bit errors or the BER-1e-7 budget (1e9 bits), rounds sharded over the ranks
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    tot, rounds = pkg.sweep.mc_sweep_until(o, 11, N_SYM, SNRS, pkg.MODE_FAST, 100, 10 ** 9, args.until_round_frames, 0, rank, world)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    work = sum(t.frames for t in tot)
+    out["cfg3_philox_mc"]["until_100_errors_or_1e-7"] = {
+        "seconds": float(dt.item()), "rounds": rounds, "round_frames": args.until_round_frames, "mode": "fast",
+        "frame_points": int(work), "symbols_per_s": work * N_SYM / float(dt.item()),
+        "points": [{"snr_db": s, "bit_errors": int(t.bit_errors), "bits": int(t.bits), "ber": t.bit_errors / t.bits} for s, t in zip(SNRS, tot)],
+        "parallelism": "every round's frame range split over %d GPU(s) for every still-active SNR point; one all-reduce per round" % world}
+    return out
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -374,34 +477,30 @@ def run_gpu(args):
     host_cnt = torch.empty(counters.shape, dtype=torch.int64).pin_memory()
     bits_h = torch.empty(bits.shape, dtype=torch.int32).pin_memory(); bits_h.copy_(bits)
     g_h = torch.empty(g.shape, dtype=torch.float32).pin_memory(); g_h.copy_(g)
+    snr_arr = np.ascontiguousarray(SNRS, dtype=np.float32)
     torch.cuda.synchronize()
     lib, h = o.lib, o.h
-    kernel_ms = []
 
     def sweep_resident(record):
+        """Transmitter once, then the whole SNR list in one kernel; returns the (start, end) events around the sweep kernel"""
         counters.zero_()
         o._check(lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), power.data_ptr(), n_frames, N_SYM, pkg.MODE_EXACT))
-        evs = []
-        for i, s in enumerate(SNRS):
-            if record:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
-            o._check(lib.ofdm_awgn_rx_inject(h, frames.data_ptr(), g.data_ptr(), power.data_ptr(), bits.data_ptr(), s,
-                                             n_frames, N_SYM, pkg.MODE_EXACT, counters[i].data_ptr(), None))
-            if record:
-                e1.record(); evs.append((e0, e1))
+        ev = None
+        if record:
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+        o._check(lib.ofdm_awgn_rx_inject_sweep(h, frames.data_ptr(), g.data_ptr(), power.data_ptr(), bits.data_ptr(), snr_arr.ctypes.data, n_snr,
+                                               n_frames, N_SYM, pkg.MODE_EXACT, counters.data_ptr()))
+        if record:
+            e1.record(); ev = (e0, e1)
         if world > 1:
-            ints = counters[:, :5].contiguous(); dist.all_reduce(ints); counters[:, :5] = ints          # integer totals
-            fl = counters[:, 5:].contiguous().view(torch.float64); dist.all_reduce(fl)                   # double sums
-            counters[:, 5:] = fl.view(torch.int64)
+            pkg.sweep.allreduce_counter_tensor(counters)
         host_cnt.copy_(counters, non_blocking=True)
-        return evs
+        return ev
 
     def sweep_host():
         res = o.sweep_inject_host(bits_h, g_h, n_frames, N_SYM, SNRS, pkg.MODE_EXACT)
         if world > 1:
-            t = torch.tensor([[c.bit_errors, c.bits, c.frames_in_error, c.rail_errors, c.frames] for c in res],
-                             dtype=torch.int64, device=dev)
-            dist.all_reduce(t)
+            res = pkg.sweep.allreduce_counters(res, device=dev)
         return res
 
     def barrier():
@@ -420,16 +519,32 @@ def run_gpu(args):
     o.replayed_frames(reset=True)
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    all_evs = []
+    sweep_evs = []
     for _ in range(args.steps):
-        all_evs += sweep_resident(True)
+        sweep_evs.append(sweep_resident(True))
     t1.record()
     barrier()
     launches = o.launch_count - launches0
     replayed = o.replayed_frames() / max(1, args.steps)
     ms_total = t0.elapsed_time(t1)
-    kernel_ms = [a.elapsed_time(b) for a, b in all_evs]
+    sweep_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in sweep_evs]))
     resident_counts = o.read_counters(host_cnt)
+
+    # the HBM-bound kernel of the path, one SNR point per launch (stage API): steps x 21 launches, events around each
+    staged_cnt = o.new_counters(n_snr)
+    point_evs = []
+    for rep in range(args.steps + 1):
+        staged_cnt.zero_()
+        for i, s in enumerate(SNRS):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+            o._check(lib.ofdm_awgn_rx_inject(h, frames.data_ptr(), g.data_ptr(), power.data_ptr(), bits.data_ptr(), s,
+                                             n_frames, N_SYM, pkg.MODE_EXACT, staged_cnt[i].data_ptr(), None))
+            e1.record()
+            if rep > 0:
+                point_evs.append((e0, e1))
+    torch.cuda.synchronize()
+    kernel_ms = [a.elapsed_time(b) for a, b in point_evs]
+    staged_counts = o.read_counters(staged_cnt)
 
     # end to end through the public host-buffer API
     for _ in range(max(1, args.warmup // 2)):
@@ -445,16 +560,26 @@ def run_gpu(args):
     e2e_ms_total = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)   # wall clock covers the host side of the call
     clocks = sampler.stop() if rank == 0 else None
 
+    g_h = bits_h = None              # release the pinned host buffers
+    configs = run_configs(o, pkg, torch, dist, dev, args, rank, world) if not args.no_configs else None
     extras = run_extras(o, pkg, torch, dev, args, rank, world) if args.extras else None
     tm = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms_total = tm.tolist()
+    # every route must agree on every integer total: all-SNR kernel == one launch per point (this rank's frames), and the
+    # all-reduced totals of the resident and the host-buffer sweeps (all ranks' frames)
+    local_res = resident_counts if world == 1 else None
+    for i, b in enumerate(staged_counts):
+        assert b.frames == n_frames and b.bits == n_frames * 96 * N_SYM
+        if local_res is not None:
+            a = local_res[i]
+            assert (a.bit_errors, a.rail_errors, a.frames_in_error) == (b.bit_errors, b.rail_errors, b.frames_in_error), "fused vs per-point"
+    for a, b in zip(resident_counts, e2e_counts):
+        assert a.frames == world * n_frames and a.bits == world * n_frames * 96 * N_SYM, "all-reduced frame / bit totals"
+        assert (a.bit_errors, a.rail_errors, a.frames_in_error, a.frames, a.bits) == (b.bit_errors, b.rail_errors, b.frames_in_error, b.frames, b.bits), \
+            "resident vs host-buffer sweep"
     if rank == 0:
-        # the two paths must agree on every integer total (single GPU: same frames)
-        if world == 1:
-            for a, b in zip(resident_counts, e2e_counts):
-                assert (a.bit_errors, a.rail_errors, a.frames_in_error) == (b.bit_errors, b.rail_errors, b.frames_in_error)
         symbols = n_frames * N_SYM * n_snr * world
         ms_step = ms_total / args.steps
         value = symbols / (ms_step * 1e-3)
@@ -470,6 +595,7 @@ def run_gpu(args):
                 if traffic is not None and n_frames != 1_000_000:
                     traffic = traffic * n_frames / 1_000_000        # captured on the 1 M-frame launch
         ber = [c.bit_errors / max(1, c.bits) for c in resident_counts]
+        km = kernel_metrics()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32+f64", "data": "synthetic",
@@ -480,18 +606,26 @@ def run_gpu(args):
                            "host_affinity": affinity},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_total / args.steps,
                         # the draws of the guard interval / cyclic prefixes are never read by the receiver and stay on the host
-                        "h2d_bytes_per_step": int(bits_h.numel() * 4 + n_frames * (128 + 64 * N_SYM) * 4),
-                        "host_buffer_bytes": int(bits_h.numel() * 4 + g_h.numel() * 4),
+                        "h2d_bytes_per_step": int(n_frames * N_SYM * 12 + n_frames * (128 + 64 * N_SYM) * 4),
+                        "host_buffer_bytes": int(n_frames * N_SYM * 12 + n_frames * flen * 4),
                         "d2h_bytes_per_step": int(n_snr * pkg.COUNTERS_BYTES)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_stream_rx2<checked,inject>", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "bytes_per_launch": BYTES_PER_FRAME_PASS * n_frames, "kernel_ms": k_ms,
-                             "kernel_share_of_step": k_ms * n_snr / ms_step,
-                             "frames_replayed_exactly_per_sweep": replayed,
-                             "frames_per_sweep": n_frames * n_snr},
+                             "timed": "%d launches (one per SNR point, %d sweeps) through ofdm_awgn_rx_inject in this run, CUDA events per launch"
+                                      % (len(kernel_ms), args.steps),
+                             "sweep_ms_if_launched_per_point": k_ms * n_snr},
+                "sweep_kernel": dict({"kernel": "k_sweep_lin<checked>", "kernel_ms": sweep_kernel_ms, "share_of_step": sweep_kernel_ms / ms_step,
+                                      "bound": "instruction issue (the frame and its draws cross HBM once per sweep)",
+                                      "hbm_GBps": BYTES_PER_FRAME_PASS * n_frames / (sweep_kernel_ms * 1e-3) / 1e9,
+                                      "frame_points_per_s": n_frames * n_snr / (sweep_kernel_ms * 1e-3),
+                                      "points_replayed_exactly_per_sweep": replayed, "frame_points_per_sweep": n_frames * n_snr},
+                                     **km.get("k_sweep_lin_checked", {})),
                 "clocks": clocks,
                 "ber_0_10_20dB": [ber[0], ber[10], ber[20]]}
+        if configs:
+            line["configs"] = configs
         if extras:
             line["extras"] = extras
         if not args.no_cpu and world == 1:
@@ -526,7 +660,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also measure configs[2] (streaming) and configs[3] (Philox MC)")
     ap.add_argument("--stream-frames", type=int, default=8_388_608, help="frames for the streaming extra (16 Mi data symbols)")
-    ap.add_argument("--mc-frames", type=int, default=2_000_000)
+    ap.add_argument("--mc-frames", type=int, default=2_000_000, help="frames per GPU of the configs[3] / configs[4] Monte-Carlo sweeps")
+    ap.add_argument("--until-round-frames", type=int, default=1 << 20, help="frames per round (all ranks together) of the until-rule sweep")
+    ap.add_argument("--no-configs", action="store_true", help="skip configs[2] / [3] / [4] (A/B runs of the headline only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

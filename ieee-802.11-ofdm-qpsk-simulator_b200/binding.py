@@ -87,10 +87,19 @@ SIGNATURES = {
     "ofdm_rx_frames": (_I, [_VP, _VP, _VP, _L, _I, _I, _VP, C.POINTER(RxDump)]),
     "ofdm_awgn_rx_inject": (_I, [_VP, _VP, _VP, _VP, _VP, _F, _L, _I, _I, _VP, C.POINTER(RxDump)]),
     "ofdm_awgn_rx_philox": (_I, [_VP, _VP, _VP, _VP, _F, _U32, _U32, _U64, _L, _I, _I, _VP, C.POINTER(RxDump)]),
+    "ofdm_awgn_rx_inject_sweep": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _L, _I, _I, _VP]),
+    "ofdm_strip_cp": (_I, [_VP, _VP, _VP, _L, _I, _I, _I]),
+    "ofdm_channel_estimate": (_I, [_VP, _VP, _VP, _L, _I, _I, _I]),
+    "ofdm_equalize": (_I, [_VP, _VP, _VP, _VP, _L, _I, _I]),
+    "ofdm_demap": (_I, [_VP, _VP, _VP, _L]),
+    "ofdm_agc_slicer": (_I, [_VP, _VP, _VP, _L]),
+    "ofdm_qpsk_demodulate": (_I, [_VP, _VP, _VP, _L]),
     "ofdm_sweep_inject_host": (_I, [_VP, _VP, _VP, _L, _I, _VP, _I, _I, C.POINTER(Counters)]),
     "ofdm_sweep_inject_dev": (_I, [_VP, _VP, _VP, _L, _I, _VP, _I, _I, C.POINTER(Counters)]),
     "ofdm_random_bits": (_I, [_VP, _U32, _U64, _L, _I, _VP]),
     "ofdm_mc_sweep_philox_dev": (_I, [_VP, _U32, _U64, _L, _I, _VP, _I, _I, _VP]),
+    "ofdm_mc_sweep_points_dev": (_I, [_VP, _U32, _U64, _L, _I, _I, _VP, _VP, _I, _I, _VP]),
+    "ofdm_mc_sweep_until": (_I, [_VP, _U32, _U64, _I, _I, _VP, _I, _I, _U64, _U64, _L, C.POINTER(Counters), C.POINTER(_I)]),
     "ofdm_mc_sweep_philox": (_I, [_VP, _U32, _U64, _L, _I, _VP, _I, _I, C.POINTER(Counters)]),
     "ofdm_multipath_taps": (_I, [_VP, _VP, _VP, _I, _VP, _L, _I]),
     "ofdm_multipath_philox": (_I, [_VP, _VP, _U32, _U64, _I, _VP, _VP, _L, _I]),
@@ -328,6 +337,51 @@ class Ofdm:
             return None, bufs
         return self.read_counters(cnt)[0], bufs
 
+    def awgn_rx_inject_sweep(self, tx, g, tx_packed, snr_db, n_sym, mode, power=None, counters=None):
+        """channel + receiver over a list of SNR points on resident frames; counters [n_snr] device tensor (accumulated into)"""
+        snr = np.ascontiguousarray(snr_db, dtype=np.float32)
+        cnt = counters if counters is not None else self.new_counters(len(snr))
+        self._check(self.lib.ofdm_awgn_rx_inject_sweep(self.h, _ptr(tx), _ptr(g), _ptr(power), _ptr(tx_packed), snr.ctypes.data, len(snr),
+                                                       tx.shape[0], n_sym, mode, _ptr(cnt)))
+        return None if counters is not None else self.read_counters(cnt)
+
+    # ---- the receiver's stages one by one
+    def strip_cp(self, frames, n_sym, data_off=160):
+        n, length = frames.shape[0], frames.shape[1]
+        out = self.empty((n, n_sym, 64, 2), self.torch.float32)
+        self._check(self.lib.ofdm_strip_cp(self.h, _ptr(frames), _ptr(out), n, n_sym, length, data_off))
+        return out
+
+    def channel_estimate(self, frames, mode, lts_off=0):
+        n, length = frames.shape[0], frames.shape[1]
+        out = self.empty((n, 64, 2), self.torch.float32)
+        self._check(self.lib.ofdm_channel_estimate(self.h, _ptr(frames), _ptr(out), n, length, lts_off, mode))
+        return out
+
+    def equalize(self, F, H, mode):
+        n, n_sym = F.shape[0], F.shape[1]
+        out = self.empty(tuple(F.shape), self.torch.float32)
+        self._check(self.lib.ofdm_equalize(self.h, _ptr(F), _ptr(H), _ptr(out), n, n_sym, mode))
+        return out
+
+    def demap(self, grid):
+        n_symbols = grid.numel() // 128
+        out = self.empty((n_symbols, 48, 2), self.torch.float32)
+        self._check(self.lib.ofdm_demap(self.h, _ptr(grid), _ptr(out), n_symbols))
+        return out
+
+    def agc_slicer(self, points):
+        n_symbols = points.numel() // 96
+        out = self.empty((n_symbols, 48, 2), self.torch.float32)
+        self._check(self.lib.ofdm_agc_slicer(self.h, _ptr(points), _ptr(out), n_symbols))
+        return out
+
+    def qpsk_demodulate(self, points):
+        n_symbols = points.numel() // 96
+        out = self.empty((n_symbols * 3,), self.torch.int32)
+        self._check(self.lib.ofdm_qpsk_demodulate(self.h, _ptr(points), _ptr(out), n_symbols))
+        return out
+
     # ---- sweeps
     def sweep_inject_host(self, bits_packed_host, g_host, n_frames, n_sym, snr_db, mode):
         """bits_packed_host / g_host: numpy arrays or pinned CPU torch tensors (HOST memory)."""
@@ -360,6 +414,23 @@ class Ofdm:
         out = (Counters * len(snr))()
         self._check(self.lib.ofdm_mc_sweep_philox(self.h, seed, frame0, n_frames, n_sym, snr.ctypes.data, len(snr), mode, out))
         return list(out)
+
+    def mc_sweep_points(self, seed, frame0, n_frames, n_sym, n_taps, snr_db, streams, mode, counters):
+        """Monte-Carlo over an explicit list of points (streams: their Philox noise streams, None = 0..n-1); n_taps = 0 is AWGN only.
+        Accumulates into the device counters tensor."""
+        snr = np.ascontiguousarray(snr_db, dtype=np.float32)
+        st = None if streams is None else np.ascontiguousarray(streams, dtype=np.uint32)
+        self._check(self.lib.ofdm_mc_sweep_points_dev(self.h, seed, frame0, n_frames, n_sym, n_taps, snr.ctypes.data,
+                                                      None if st is None else st.ctypes.data, len(snr), mode, _ptr(counters)))
+
+    def mc_sweep_until(self, seed, frame0, n_sym, n_taps, snr_db, mode, target_errors=100, max_bits=10 ** 9, round_frames=1 << 20):
+        """configs[3]'s stop rule on one GPU: returns (host totals, rounds)"""
+        snr = np.ascontiguousarray(snr_db, dtype=np.float32)
+        out = (Counters * len(snr))()
+        rounds = _I(0)
+        self._check(self.lib.ofdm_mc_sweep_until(self.h, seed, frame0, n_sym, n_taps, snr.ctypes.data, len(snr), mode, target_errors, max_bits,
+                                                 round_frames, out, C.byref(rounds)))
+        return list(out), int(rounds.value)
 
     def multipath_taps(self, tx, taps, n_sym):
         out = self.empty(tuple(tx.shape), self.torch.float32)

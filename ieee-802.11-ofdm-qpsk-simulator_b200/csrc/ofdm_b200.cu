@@ -8,6 +8,7 @@
 #include <new>
 
 #include "ofdm_chain.cuh"
+#include "ofdm_sweep.cuh"
 
 using namespace ofdm;
 
@@ -23,6 +24,7 @@ struct ofdm_ctx {
     bool checked = true;             // EXACT sweeps speculate in fp32, verify, and replay exactly (kArithChecked)
     bool force_replay = false;       // testing knob: the verification fails every frame
     bool general_stream = false;     // testing knob: two-symbol frames through the multi-pass streaming kernel too
+    bool fused_sweep = true;         // ofdm_sweep_inject_*: the all-SNR kernel k_sweep_lin (default frame shape) instead of one launch per SNR point
     int multipath_path = 0;          // configs[4]: 0 = auto (fast: fused on-chip kernel, exact: HBM-staged frames), 1 = staged, 2 = fused
     char err[256] = {0};
     float lts_freq[128];
@@ -285,6 +287,11 @@ int frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames,
     return check_launch(ctx, "k_frame_power_fast");
 }
 
+// Channel + receiver of a whole SNR list on resident frames: the all-SNR kernel when it applies (two-symbol frames, 16-byte
+// aligned buffers, speculation allowed), else one fused channel+receiver launch per SNR point.  counters [n_snr], accumulated into.
+int sweep_points(ofdm_ctx *ctx, const float *frames, const float *g, const float *power, const uint32_t *bits, long n_frames, int n_sym,
+                 const float *snr_db, int n_snr, int mode, ofdm_counters *counters);
+
 bool mode_ok(int mode) { return mode == OFDM_MODE_EXACT || mode == OFDM_MODE_FAST; }
 bool nsym_ok(int n_sym) { return n_sym >= 1 && n_sym <= OFDM_MAX_SYM; }
 
@@ -434,6 +441,7 @@ int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "force_generic_rx")) { ctx->force_generic = value != 0; return OFDM_OK; }
     if (!strcmp(name, "exact_speculation")) { ctx->checked = value != 0; return OFDM_OK; }
     if (!strcmp(name, "force_replay")) { ctx->force_replay = value != 0; return OFDM_OK; }
+    if (!strcmp(name, "fused_sweep")) { ctx->fused_sweep = value != 0; return OFDM_OK; }
     if (!strcmp(name, "general_stream")) { ctx->general_stream = value != 0; return OFDM_OK; }
     if (!strcmp(name, "multipath_path")) { if (value < 0 || value > 2) return fail(ctx, OFDM_ERR_INVALID, "multipath_path: 0..2"); ctx->multipath_path = value; return OFDM_OK; }
     return fail(ctx, OFDM_ERR_INVALID, "unknown option");
@@ -696,6 +704,90 @@ int ofdm_awgn_rx_philox(ofdm_ctx *ctx, const float *tx, const float *power, cons
                      counters, dump);
 }
 
+int ofdm_awgn_rx_inject_sweep(ofdm_ctx *ctx, const float *tx, const float *g, const float *power, const uint32_t *tx_bits, const float *snr_db,
+                              int n_snr, long n_frames, int n_sym, int mode, ofdm_counters *counters)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0);
+    if (n_frames == 0 || n_snr == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, tx != nullptr && g != nullptr && tx_bits != nullptr && snr_db != nullptr && counters != nullptr);
+    const float *pw = nullptr;
+    if (int st = resolve_power(ctx, tx, power, n_frames, OFDM_FRAME_LEN(n_sym), mode, &pw)) return st;
+    return sweep_points(ctx, tx, g, pw, tx_bits, n_frames, n_sym, snr_db, n_snr, mode, counters);
+}
+
+// ------------------------------------------------------------------ the receiver's stages one by one
+int ofdm_strip_cp(ofdm_ctx *ctx, const float *frames, float *bodies, long n_frames, int n_sym, int frame_len, int data_off)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && data_off >= 0 && frame_len >= data_off + 80 * n_sym);
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, frames != nullptr && bodies != nullptr && frames != bodies);
+    const long n = n_frames * n_sym * 64;
+    k_strip_cp<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), reinterpret_cast<float2 *>(bodies), n, n_sym, frame_len, data_off);
+    return check_launch(ctx, "k_strip_cp");
+}
+int ofdm_channel_estimate(ofdm_ctx *ctx, const float *frames, float *H, long n_frames, int frame_len, int lts_off, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && mode_ok(mode) && lts_off >= 0 && frame_len >= lts_off + 160);
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, frames != nullptr && H != nullptr && frames != H);
+    const float2 *x = reinterpret_cast<const float2 *>(frames);
+    float2 *h = reinterpret_cast<float2 *>(H);
+    if (mode == OFDM_MODE_EXACT) {
+        int grid = grid_for(ctx, k_channel_estimate<true>, 0, kWarpsPerBlock * 2, n_frames);
+        k_channel_estimate<true><<<grid, kThreads, 0, ctx->stream>>>(x, h, n_frames, frame_len, lts_off);
+    } else {
+        int grid = grid_for(ctx, k_channel_estimate<false>, 0, kWarpsPerBlock * 2, n_frames);
+        k_channel_estimate<false><<<grid, kThreads, 0, ctx->stream>>>(x, h, n_frames, frame_len, lts_off);
+    }
+    return check_launch(ctx, "k_channel_estimate");
+}
+int ofdm_equalize(ofdm_ctx *ctx, const float *F, const float *H, float *E, long n_frames, int n_sym, int mode)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode));
+    if (n_frames == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, F != nullptr && H != nullptr && E != nullptr);
+    const long n = n_frames * n_sym * 64;
+    if (mode == OFDM_MODE_EXACT)
+        k_equalize<true><<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(F), reinterpret_cast<const float2 *>(H), reinterpret_cast<float2 *>(E), n, n_sym);
+    else
+        k_equalize<false><<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(F), reinterpret_cast<const float2 *>(H), reinterpret_cast<float2 *>(E), n, n_sym);
+    return check_launch(ctx, "k_equalize");
+}
+int ofdm_demap(ofdm_ctx *ctx, const float *grid, float *points, long n_symbols)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_symbols >= 0);
+    if (n_symbols == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, grid != nullptr && points != nullptr && grid != points);
+    const long n = n_symbols * 48;
+    k_demap<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(grid), reinterpret_cast<float2 *>(points), n);
+    return check_launch(ctx, "k_demap");
+}
+int ofdm_agc_slicer(ofdm_ctx *ctx, const float *points, float *sliced, long n_symbols)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_symbols >= 0);
+    if (n_symbols == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, points != nullptr && sliced != nullptr);
+    const long n = n_symbols * 48;
+    k_agc_slicer<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(points), reinterpret_cast<float2 *>(sliced), n);
+    return check_launch(ctx, "k_agc_slicer");
+}
+int ofdm_qpsk_demodulate(ofdm_ctx *ctx, const float *points, uint32_t *bits, long n_symbols)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_symbols >= 0);
+    if (n_symbols == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, points != nullptr && bits != nullptr);
+    const long n = n_symbols * 3;
+    k_qpsk_demod<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(points), bits, n);
+    return check_launch(ctx, "k_qpsk_demod");
+}
+
 // ------------------------------------------------------------------ sweep drivers
 int ofdm_sweep_inject_dev(ofdm_ctx *ctx, const uint32_t *bits, const float *g, long n_frames, int n_sym,
                           const float *snr_db, int n_snr, int mode, ofdm_counters *out_host)
@@ -703,7 +795,7 @@ int ofdm_sweep_inject_dev(ofdm_ctx *ctx, const uint32_t *bits, const float *g, l
     if (int st = bind(ctx)) return st;
     OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0);
     OFDM_REQUIRE(ctx, n_snr == 0 || (snr_db != nullptr && out_host != nullptr));
-    memset(out_host, 0, sizeof(ofdm_counters) * (size_t)n_snr);
+    if (n_snr > 0) memset(out_host, 0, sizeof(ofdm_counters) * (size_t)n_snr);
     if (n_frames == 0 || n_snr == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, bits != nullptr && g != nullptr);
     const int len = OFDM_FRAME_LEN(n_sym);
@@ -714,11 +806,8 @@ int ofdm_sweep_inject_dev(ofdm_ctx *ctx, const uint32_t *bits, const float *g, l
     OFDM_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(ofdm_counters) * (size_t)n_snr, ctx->stream));
     // Transmitter() runs once (OFDM.c:1191); the SNR loop (OFDM.c:1202-1222) reruns channel + receiver
     if (int st = ofdm_tx_frames(ctx, bits, (float *)frames, (float *)power, n_frames, n_sym, mode)) return st;
-    for (int i = 0; i < n_snr; ++i) {
-        if (int st = ofdm_awgn_rx_inject(ctx, (const float *)frames, g, (const float *)power, bits, snr_db[i], n_frames, n_sym,
-                                         mode, (ofdm_counters *)cnt + i, nullptr))
-            return st;
-    }
+    if (int st = sweep_points(ctx, (const float *)frames, g, (const float *)power, bits, n_frames, n_sym, snr_db, n_snr, mode, (ofdm_counters *)cnt))
+        return st;
     OFDM_CUDA(ctx, cudaMemcpyAsync(out_host, cnt, sizeof(ofdm_counters) * (size_t)n_snr, cudaMemcpyDeviceToHost, ctx->stream));
     OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return OFDM_OK;
@@ -773,15 +862,58 @@ int ofdm_sweep_inject_host(ofdm_ctx *ctx, const uint32_t *bits_host, const float
         OFDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[c & 1], 0));
         float *fr = (float *)frames + f0 * len * 2, *pw = (float *)power + f0;
         if (int st = ofdm_tx_frames(ctx, (const uint32_t *)db, fr, pw, n, n_sym, mode)) return st;        // Transmitter(), OFDM.c:1191
-        for (int i = 0; i < n_snr; ++i)                                                                   // SNR loop, OFDM.c:1202-1222
-            if (int st = ofdm_awgn_rx_inject(ctx, fr, (const float *)dg, pw, (const uint32_t *)db, snr_db[i], n, n_sym, mode,
-                                             (ofdm_counters *)cnt + i, nullptr))
-                return st;
+        if (int st = sweep_points(ctx, fr, (const float *)dg, pw, (const uint32_t *)db, n, n_sym, snr_db, n_snr, mode,     // SNR loop, OFDM.c:1202-1222
+                                  (ofdm_counters *)cnt))
+            return st;
     }
     OFDM_CUDA(ctx, cudaMemcpyAsync(out_host, cnt, sizeof(ofdm_counters) * (size_t)n_snr, cudaMemcpyDeviceToHost, ctx->stream));
     OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return OFDM_OK;
 }
+
+}  // extern "C"
+
+namespace {
+int sweep_points(ofdm_ctx *ctx, const float *frames, const float *g, const float *power, const uint32_t *bits, long n_frames, int n_sym,
+                 const float *snr_db, int n_snr, int mode, ofdm_counters *counters)
+{
+    const bool aligned = ((uintptr_t)frames % 16 == 0) && ((uintptr_t)g % 16 == 0);
+    const bool fused = ctx->fused_sweep && n_sym == 2 && aligned && !ctx->force_generic && !ctx->general_stream &&
+                       (mode != OFDM_MODE_EXACT || ctx->checked);
+    if (!fused) {
+        for (int i = 0; i < n_snr; ++i)
+            if (int st = ofdm_awgn_rx_inject(ctx, frames, g, power, bits, snr_db[i], n_frames, n_sym, mode, counters + i, nullptr)) return st;
+        return OFDM_OK;
+    }
+    const size_t smem = sweep_smem_bytes();
+    const long max_frames = 1L << 30;                      // per launch: the per-lane totals are 32-bit
+    for (int s0 = 0; s0 < n_snr; s0 += kMaxSnr) {
+        SweepParams p;
+        memset(&p, 0, sizeof p);
+        p.n_snr = n_snr - s0 < kMaxSnr ? n_snr - s0 : kMaxSnr;
+        for (int i = 0; i < p.n_snr; ++i) p.snr_lin[i] = snr_linear(snr_db[s0 + i]);
+        p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+        p.counters = counters + s0;
+        for (long f0 = 0; f0 < n_frames; f0 += max_frames) {
+            p.n_frames = n_frames - f0 < max_frames ? n_frames - f0 : max_frames;
+            p.in = reinterpret_cast<const float2 *>(frames) + f0 * 320;
+            p.g = g + f0 * 320;
+            p.power = power + f0;
+            p.tx_bits = bits + f0 * 6;
+            auto launch = [&](auto k) -> int {
+                OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
+                k<<<grid, kThreads, smem, ctx->stream>>>(p);
+                return check_launch(ctx, "k_sweep_lin");
+            };
+            if (int st = mode == OFDM_MODE_EXACT ? launch(k_sweep_lin<kArithChecked>) : launch(k_sweep_lin<kArithFast>)) return st;
+        }
+    }
+    return OFDM_OK;
+}
+}  // namespace
+
+extern "C" {
 
 // ------------------------------------------------------------------ Philox Monte-Carlo
 int ofdm_random_bits(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, uint32_t *bits)
@@ -795,37 +927,45 @@ int ofdm_random_bits(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frame
     return check_launch(ctx, "k_philox_bits");
 }
 
-int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, const float *snr_db,
-                             int n_snr, int mode, ofdm_counters *counters)
+}  // extern "C"
+
+namespace {
+// AWGN Monte-Carlo over a list of points; streams[i] (nullable: i) is the Philox noise stream of point i
+int mc_awgn_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, const float *snr_db, const uint32_t *streams,
+                 int n_snr, int mode, ofdm_counters *counters)
 {
-    if (int st = bind(ctx)) return st;
-    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0 && n_snr <= kMaxSnr);
-    if (n_frames == 0 || n_snr == 0) return OFDM_OK;
-    OFDM_REQUIRE(ctx, snr_db != nullptr && counters != nullptr);
     if (n_sym == 2) {
-        McParams p;
-        memset(&p, 0, sizeof p);
-        p.seed = seed; p.frame0 = frame0; p.n_frames = n_frames; p.n_snr = n_snr; p.counters = counters;
-        for (int i = 0; i < n_snr; ++i) { p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i])); }
         const size_t smem = mc_smem_bytes();
-        p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
-        p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
-        auto launch = [&](auto k) -> int {
-            OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int grid = grid_for(ctx, k, smem, kWarpsPerBlock, n_frames);
-            k<<<grid, kThreads, smem, ctx->stream>>>(p);
-            return OFDM_OK;
-        };
-        int st;
-        if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast>);
-        else if (ctx->checked) st = launch(k_mc_philox<kArithChecked>);
-        else st = launch(k_mc_philox<kArithExact>);
-        if (st) return st;
-        return check_launch(ctx, "k_mc_philox");
+        const long max_frames = 1L << 30;                  // per launch: the per-lane totals are 32-bit
+        for (long f0 = 0; f0 < n_frames; f0 += max_frames) {
+            McParams p;
+            memset(&p, 0, sizeof p);
+            p.seed = seed; p.frame0 = frame0 + (uint64_t)f0; p.n_frames = n_frames - f0 < max_frames ? n_frames - f0 : max_frames;
+            p.n_snr = n_snr; p.counters = counters;
+            for (int i = 0; i < n_snr; ++i) {
+                p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i]));
+                p.stream[i] = streams ? streams[i] : (uint32_t)i;
+            }
+            p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+            p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
+            auto launch = [&](auto k) -> int {
+                OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
+                k<<<grid, kThreads, smem, ctx->stream>>>(p);
+                return check_launch(ctx, "k_mc_philox");
+            };
+            int st;
+            if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast>);
+            else if (ctx->checked) st = launch(k_mc_philox<kArithChecked>);
+            else st = launch(k_mc_philox<kArithExact>);
+            if (st) return st;
+        }
+        return OFDM_OK;
     }
-    // other frame shapes: the same streams through the staged kernels, in chunks that bound the scratch memory
+    // other frame shapes: the same streams through the staged kernels, in chunks that bound the scratch memory (2 GiB of frames)
     const int len = OFDM_FRAME_LEN(n_sym);
-    const long chunk = 262144;
+    long chunk = (2L << 30) / ((long)len * 8);
+    if (chunk < 1024) chunk = 1024;
     for (long f0 = 0; f0 < n_frames; f0 += chunk) {
         const long n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         void *bits = nullptr, *frames = nullptr, *power = nullptr;
@@ -836,9 +976,74 @@ int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long
         if (int st = ofdm_tx_frames(ctx, (const uint32_t *)bits, (float *)frames, (float *)power, n, n_sym, mode)) return st;
         for (int i = 0; i < n_snr; ++i)
             if (int st = ofdm_awgn_rx_philox(ctx, (const float *)frames, (const float *)power, (const uint32_t *)bits, snr_db[i], seed,
-                                             (uint32_t)i, frame0 + (uint64_t)f0, n, n_sym, mode, counters + i, nullptr))
+                                             streams ? streams[i] : (uint32_t)i, frame0 + (uint64_t)f0, n, n_sym, mode, counters + i, nullptr))
                 return st;
     }
+    return OFDM_OK;
+}
+int mc_multipath_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps, const float *snr_db,
+                      const uint32_t *streams, int n_snr, int mode, ofdm_counters *counters);
+}  // namespace
+
+extern "C" {
+
+int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, const float *snr_db,
+                             int n_snr, int mode, ofdm_counters *counters)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0 && n_snr <= kMaxSnr);
+    if (n_frames == 0 || n_snr == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, snr_db != nullptr && counters != nullptr);
+    return mc_awgn_core(ctx, seed, frame0, n_frames, n_sym, snr_db, nullptr, n_snr, mode, counters);
+}
+
+int ofdm_mc_sweep_points_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps, const float *snr_db,
+                             const uint32_t *streams, int n_points, int mode, ofdm_counters *counters)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_points >= 0 && n_points <= kMaxSnr && n_taps >= 0 && n_taps <= kMaxTaps);
+    if (n_frames == 0 || n_points == 0) return OFDM_OK;
+    OFDM_REQUIRE(ctx, snr_db != nullptr && counters != nullptr);
+    if (n_taps > 0) return mc_multipath_core(ctx, seed, frame0, n_frames, n_sym, n_taps, snr_db, streams, n_points, mode, counters);
+    return mc_awgn_core(ctx, seed, frame0, n_frames, n_sym, snr_db, streams, n_points, mode, counters);
+}
+
+int ofdm_mc_sweep_until(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, int n_sym, int n_taps, const float *snr_db, int n_snr, int mode,
+                        uint64_t target_errors, uint64_t max_bits, long round_frames, ofdm_counters *out_host, int *rounds_out)
+{
+    if (int st = bind(ctx)) return st;
+    OFDM_REQUIRE(ctx, nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0 && n_snr <= kMaxSnr && n_taps >= 0 && n_taps <= kMaxTaps);
+    OFDM_REQUIRE(ctx, round_frames >= 1 && max_bits >= 1 && (n_snr == 0 || (snr_db != nullptr && out_host != nullptr)));
+    if (rounds_out) *rounds_out = 0;
+    if (n_snr == 0) return OFDM_OK;
+    memset(out_host, 0, sizeof(ofdm_counters) * (size_t)n_snr);
+    void *cnt = nullptr;
+    if (int st = ensure_scratch(ctx, 3, sizeof(ofdm_counters) * (size_t)kMaxSnr, &cnt)) return st;
+    int active[kMaxSnr], n_active = n_snr, rounds = 0;
+    for (int i = 0; i < n_snr; ++i) active[i] = i;
+    ofdm_counters part[kMaxSnr];
+    while (n_active > 0) {
+        float snr_a[kMaxSnr];
+        uint32_t stream_a[kMaxSnr];
+        for (int j = 0; j < n_active; ++j) { snr_a[j] = snr_db[active[j]]; stream_a[j] = (uint32_t)active[j]; }
+        OFDM_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(ofdm_counters) * (size_t)n_active, ctx->stream));
+        if (int st = ofdm_mc_sweep_points_dev(ctx, seed, frame0 + (uint64_t)rounds * (uint64_t)round_frames, round_frames, n_sym, n_taps, snr_a, stream_a,
+                                              n_active, mode, (ofdm_counters *)cnt))
+            return st;
+        OFDM_CUDA(ctx, cudaMemcpyAsync(part, cnt, sizeof(ofdm_counters) * (size_t)n_active, cudaMemcpyDeviceToHost, ctx->stream));
+        OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int keep = 0;
+        for (int j = 0; j < n_active; ++j) {
+            ofdm_counters &t = out_host[active[j]];
+            const ofdm_counters &q = part[j];
+            t.bit_errors += q.bit_errors; t.bits += q.bits; t.frames_in_error += q.frames_in_error; t.rail_errors += q.rail_errors; t.frames += q.frames;
+            t.sum_err2 += q.sum_err2; t.sum_ref2 += q.sum_ref2; t.sum_evm_lin += q.sum_evm_lin;
+            if (t.bit_errors < target_errors && t.bits < max_bits) active[keep++] = active[j];   // the stop rule of configs[3]
+        }
+        n_active = keep;
+        ++rounds;
+    }
+    if (rounds_out) *rounds_out = rounds;
     return OFDM_OK;
 }
 
@@ -847,7 +1052,7 @@ int ofdm_mc_sweep_philox(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_f
 {
     if (int st = bind(ctx)) return st;
     OFDM_REQUIRE(ctx, n_snr >= 0 && n_snr <= kMaxSnr && (n_snr == 0 || out_host != nullptr));
-    memset(out_host, 0, sizeof(ofdm_counters) * (size_t)n_snr);
+    if (n_snr > 0) memset(out_host, 0, sizeof(ofdm_counters) * (size_t)n_snr);
     if (n_snr == 0 || n_frames == 0) return OFDM_OK;
     void *cnt = nullptr;
     if (int st = ensure_scratch(ctx, 3, sizeof(ofdm_counters) * (size_t)n_snr, &cnt)) return st;
@@ -899,33 +1104,51 @@ int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, l
     OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode) && n_snr >= 0 && n_snr <= kMaxSnr && n_taps >= 1 && n_taps <= kMaxTaps);
     if (n_frames == 0 || n_snr == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, snr_db != nullptr && counters != nullptr);
+    return mc_multipath_core(ctx, seed, frame0, n_frames, n_sym, n_taps, snr_db, nullptr, n_snr, mode, counters);
+}
+
+}  // extern "C"
+
+namespace {
+int mc_multipath_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps, const float *snr_db,
+                      const uint32_t *streams, int n_snr, int mode, ofdm_counters *counters)
+{
     // Measured per 1 M frames x 21 SNR points: fast 14.8 ms fused vs 16.9 ms staged; exact 27.3 ms fused vs 20.0 ms staged (the
     // fused kernel runs each frame's exact power chain on one lane, the staged path one chain per lane).
     const bool fused = ctx->multipath_path == 2 || (ctx->multipath_path == 0 && mode == OFDM_MODE_FAST);
     if (n_sym == 2 && !ctx->force_generic && fused) {
         // default frame shape: everything on chip (k_mc_philox<., true>), same totals as the staged path below
-        McParams p;
-        memset(&p, 0, sizeof p);
-        p.seed = seed; p.frame0 = frame0; p.n_frames = n_frames; p.n_snr = n_snr; p.counters = counters; p.n_taps = n_taps;
-        for (int i = 0; i < n_snr; ++i) { p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i])); }
-        p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
-        p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
         const size_t smem = mc_smem_bytes(true);
-        auto launch = [&](auto k) -> int {
-            OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int grid = grid_for(ctx, k, smem, kWarpsPerBlock, n_frames);
-            k<<<grid, kThreads, smem, ctx->stream>>>(p);
-            return OFDM_OK;
-        };
-        int st;
-        if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast, true>);
-        else if (ctx->checked) st = launch(k_mc_philox<kArithChecked, true>);
-        else st = launch(k_mc_philox<kArithExact, true>);
-        if (st) return st;
-        return check_launch(ctx, "k_mc_philox<multipath>");
+        const long max_frames = 1L << 30;
+        for (long f0 = 0; f0 < n_frames; f0 += max_frames) {
+            McParams p;
+            memset(&p, 0, sizeof p);
+            p.seed = seed; p.frame0 = frame0 + (uint64_t)f0; p.n_frames = n_frames - f0 < max_frames ? n_frames - f0 : max_frames;
+            p.n_snr = n_snr; p.counters = counters; p.n_taps = n_taps;
+            for (int i = 0; i < n_snr; ++i) {
+                p.snr_lin[i] = snr_linear(snr_db[i]); p.inv_sqrt_snr[i] = (float)(1.0 / sqrt((double)p.snr_lin[i]));
+                p.stream[i] = streams ? streams[i] : (uint32_t)i;
+            }
+            p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+            p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
+            auto launch = [&](auto k) -> int {
+                OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
+                k<<<grid, kThreads, smem, ctx->stream>>>(p);
+                return check_launch(ctx, "k_mc_philox<multipath>");
+            };
+            int st;
+            if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast, true>);
+            else if (ctx->checked) st = launch(k_mc_philox<kArithChecked, true>);
+            else st = launch(k_mc_philox<kArithExact, true>);
+            if (st) return st;
+        }
+        return OFDM_OK;
     }
+    // staged: frames in HBM once per chunk (two frame buffers of 2 GiB each)
     const int len = OFDM_FRAME_LEN(n_sym);
-    const long chunk = 1048576;
+    long chunk = (2L << 30) / ((long)len * 8);
+    if (chunk < 1024) chunk = 1024;
     for (long f0 = 0; f0 < n_frames; f0 += chunk) {
         const long n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         void *bits = nullptr, *frames = nullptr, *power = nullptr, *faded = nullptr;
@@ -940,11 +1163,14 @@ int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, l
         if (int st = frame_power(ctx, (const float *)faded, (float *)power, n, len, mode)) return st;      // power of what goes on the air
         for (int i = 0; i < n_snr; ++i)
             if (int st = ofdm_awgn_rx_philox(ctx, (const float *)faded, (const float *)power, (const uint32_t *)bits, snr_db[i], seed,
-                                             (uint32_t)i, fr0, n, n_sym, mode, counters + i, nullptr))
+                                             streams ? streams[i] : (uint32_t)i, fr0, n, n_sym, mode, counters + i, nullptr))
                 return st;
     }
     return OFDM_OK;
 }
+}  // namespace
+
+extern "C" {
 
 // ------------------------------------------------------------------ pulse shaping
 int ofdm_rrc_tx(ofdm_ctx *ctx, const float *frames, float *out, long n_frames, int frame_len)

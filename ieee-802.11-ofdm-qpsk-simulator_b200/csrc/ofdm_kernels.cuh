@@ -610,4 +610,145 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
     }
 }
 
+// ------------------------------------------------------------------ stand-alone receiver stages
+// The reference's receiver is a sequence of separate functions / inline blocks; the fused kernels above are what a
+// sweep runs, these are their 1:1 batched counterparts (device buffers in, device buffers out) so that a caller can
+// stop after any stage exactly as with the reference.
+
+// CP strip OFDM.c:1024-1031: frames [n][frame_len] -> symbol bodies [n][n_sym][64]; data_off = sample index of the
+// first data symbol (160 for LTS || data frames, 320 with the STS slot in front as in the reference's own frame)
+__global__ void k_strip_cp(const float2 *__restrict__ frames, float2 *__restrict__ out, long n_out, int n_sym, int frame_len, int data_off)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const long per = (long)n_sym * 64;
+    const long f = i / per; const int r = (int)(i - f * per), s = r >> 6, k = r & 63;
+    out[i] = frames[f * frame_len + data_off + 80 * s + 16 + k];
+}
+
+// Channel_Estimation OFDM.c:830-850: fft of the two LTS halves (samples lts_off + 32 .. + 95 and + 96 .. + 159 of each
+// frame), H[c] = 0.5 * (A[c] + B[c]) * conj(L[c]) on the centred grid.  EXACT evaluates the product as gcc does for
+// `double * float complex * float complex` -- (0.5 re, 0.5 im) then the full complex multiply by (L, -0) in double, one
+// rounding to float -- so that even the signs of zeros (null bins, cancelling halves) are the reference's.
+// A warp serves two frames: lane group 2k + h transforms half h of frame k.
+template <bool EXACT>
+__global__ void __launch_bounds__(kThreads) k_channel_estimate(const float2 *__restrict__ frames, float2 *__restrict__ H, long n_frames,
+                                                               int frame_len, int lts_off)
+{
+    __shared__ float2 s_tile[kWarpsPerBlock][kWarpTile];
+    __shared__ float2 s_b[kWarpsPerBlock][2][72];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    float2 *tile = s_tile[warp] + grp * kGroupPitch;
+    Tw<EXACT> tw; tw.load(u);
+    const long n_pairs = (n_frames + 1) / 2;
+    for (long pr = (long)blockIdx.x * kWarpsPerBlock + warp; pr < n_pairs; pr += (long)gridDim.x * kWarpsPerBlock) {
+        const long f = 2 * pr + (grp >> 1);
+        const bool active = f < n_frames;
+        const int n0 = lts_off + 32 + 64 * (grp & 1);
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = active ? frames[f * frame_len + n0 + u + 8 * slot_m<EXACT>(i)] : make_float2(0.f, 0.f);
+        fft64<EXACT>(v, tw, tile, u);
+        if (grp & 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_b[warp][grp >> 1][u + 8 * j] = v[j];
+        }
+        __syncwarp();
+        if (!(grp & 1) && active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = u + 8 * j;
+                const float2 B = s_b[warp][grp >> 1][p];
+                const float l = (float)c_tab.bin_lts[p];
+                float2 h;
+                if (EXACT) {
+                    const float sr = __fadd_rn(v[j].x, B.x), si = __fadd_rn(v[j].y, B.y);
+                    const double hr = __dmul_rn(0.5, (double)sr), hi = __dmul_rn(0.5, (double)si), lr = (double)l, li = -0.0;
+                    h.x = __double2float_rn(__dsub_rn(__dmul_rn(hr, lr), __dmul_rn(hi, li)));
+                    h.y = __double2float_rn(__dadd_rn(__dmul_rn(hr, li), __dmul_rn(hi, lr)));
+                } else {
+                    h = make_float2((v[j].x + B.x) * (0.5f * l), (v[j].y + B.y) * (0.5f * l));
+                }
+                H[f * 64 + ((p + 32) & 63)] = h;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// libgcc __divsc3 (gcc 13: quotient formula in double, one rounding to float) with all three of its NaN recoveries
+__device__ __forceinline__ float2 divsc3(float2 n, float2 h)
+{
+    double a = n.x, b = n.y, c = h.x, d = h.y;
+    const double den = __dadd_rn(__dmul_rn(c, c), __dmul_rn(d, d));
+    double x = __ddiv_rn(__dadd_rn(__dmul_rn(a, c), __dmul_rn(b, d)), den);
+    double y = __ddiv_rn(__dsub_rn(__dmul_rn(b, c), __dmul_rn(a, d)), den);
+    if (isnan(x) && isnan(y)) {
+        const double inf = (double)INFINITY;
+        if (c == 0.0 && d == 0.0 && (!isnan(a) || !isnan(b))) {
+            x = __dmul_rn(copysign(inf, c), a); y = __dmul_rn(copysign(inf, c), b);
+        } else if ((isinf(a) || isinf(b)) && isfinite(c) && isfinite(d)) {
+            a = copysign(isinf(a) ? 1.0 : 0.0, a); b = copysign(isinf(b) ? 1.0 : 0.0, b);
+            x = __dmul_rn(inf, __dadd_rn(__dmul_rn(a, c), __dmul_rn(b, d)));
+            y = __dmul_rn(inf, __dsub_rn(__dmul_rn(b, c), __dmul_rn(a, d)));
+        } else if ((isinf(c) || isinf(d)) && isfinite(a) && isfinite(b)) {
+            c = copysign(isinf(c) ? 1.0 : 0.0, c); d = copysign(isinf(d) ? 1.0 : 0.0, d);
+            x = __dmul_rn(0.0, __dadd_rn(__dmul_rn(a, c), __dmul_rn(b, d)));
+            y = __dmul_rn(0.0, __dsub_rn(__dmul_rn(b, c), __dmul_rn(a, d)));
+        }
+    }
+    return make_float2(__double2float_rn(x), __double2float_rn(y));
+}
+
+// one-tap equaliser OFDM.c:1044-1052: E[f][s][c] = F[f][s][c] / H[f][c] for all 64 centred bins (the 12 null bins
+// come out as the inf / NaN the reference computes there and never reads -- SURVEY Q16)
+template <bool EXACT>
+__global__ void k_equalize(const float2 *__restrict__ F, const float2 *__restrict__ H, float2 *__restrict__ E, long n_total, int n_sym)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const long f = i / ((long)n_sym * 64);
+    const float2 h = H[f * 64 + (i & 63)];
+    E[i] = EXACT ? divsc3(F[i], h) : div_fast(F[i], h);
+}
+
+// demap OFDM.c:1059-1069: the 48 data bins of each centred 64-grid, in order
+__global__ void k_demap(const float2 *__restrict__ grid, float2 *__restrict__ out, long n_points)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    const long sym = i / 48; const int d = (int)(i - sym * 48);
+    out[i] = grid[sym * 64 + ((c_tab.data_bin[d] + 32) & 63)];
+}
+
+// AGC_Receiver OFDM.c:852-871: the hard-decision slicer -- each rail to +1/sqrt(2) if > 0 else -1/sqrt(2) (0 and NaN go negative)
+__global__ void k_agc_slicer(const float2 *__restrict__ in, float2 *__restrict__ out, long n_points)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    const float2 z = in[i];
+    out[i] = make_float2(z.x > 0.f ? kQpsk : -kQpsk, z.y > 0.f ? kQpsk : -kQpsk);
+}
+
+// QPSK_Demodulator OFDM.c:873-908 with the reference's own comparisons: (+,+) -> 00, (-,+) -> 01, (-,-) -> 10, anything else
+// (a zero or NaN rail included) -> 11; bit 2j = c, bit 2j+1 = d.  One thread per packed word (16 points).
+__global__ void k_qpsk_demod(const float2 *__restrict__ in, uint32_t *__restrict__ bits, long n_words)
+{
+    const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const float2 *z = in + w * 16;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float a = z[j].x, b = z[j].y;
+        uint32_t c, d;
+        if (a > 0.f && b > 0.f) { c = 0; d = 0; }
+        else if (a < 0.f && b > 0.f) { c = 0; d = 1; }
+        else if (a < 0.f && b < 0.f) { c = 1; d = 0; }
+        else { c = 1; d = 1; }
+        v |= (c | (d << 1)) << (2 * j);
+    }
+    bits[w] = v;
+}
+
 }  // namespace ofdm

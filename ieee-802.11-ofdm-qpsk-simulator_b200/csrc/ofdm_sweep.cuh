@@ -1,0 +1,244 @@
+// ofdm_sweep.cuh -- the injected-noise SNR sweep of configs[1] (main()'s loop OFDM.c:1202-1222 over a batch of
+// frames) in ONE kernel, k_sweep_lin.
+//
+// The sweep reuses each frame's draws g at every SNR point; only the scale sigma changes (OFDM.c:645-651).  The
+// transform is linear, so   FFT(x + sigma g) = FFT(x) + sigma FFT(g):   a frame's four windows (LTS halves, two symbol
+// bodies) and the matching four windows of draws are transformed ONCE, and every SNR point then costs one packed
+// multiply-add per bin it needs -- F = X + sigma N for the lane's three data bins, G = (X_A + X_B) + sigma (N_A + N_B)
+// for their channel estimate (:848) -- followed by the decision stage.  The frame and its draws cross HBM once per
+// sweep instead of once per SNR point (3100 B per frame instead of 21 x 3100 B), the SNR loop touches neither shared
+// memory nor the LSU, and the per-SNR totals live in registers of the lane that owns the SNR point (as in k_mc_philox).
+//
+// Exactness (OFDM_MODE_EXACT = kArithChecked) is the scheme of ofdm_chain.cuh: fp32 speculation, every rail decision
+// verified against a rigorous bound on |speculated - reference|, doubtful (frame, SNR point)s replayed in the
+// reference's arithmetic from global memory (stream_frame_replay).  The bound for this kernel, per bin of a window with
+// clean samples x, draws g and S = |x|_2 + sigma |g|_2 (u = 2^-24; |X_k| <= 8 |x|_2 by Cauchy-Schwarz):
+//   speculated  fl(X~ + sigma_f N~):  272 u |x|_2 + 272 u sigma |g|_2  (the two fp32 transforms, ofdm_chain.cuh)
+//                                     + 8 u sigma |g|_2  (sigma_f = fl32(sigma_d))  + 8 u S  (rounding of the multiply-add)
+//   reference   FFT_ref(x'), x' = fl(x + fl(sigma_d g)) (:651):  97 u |x'|_2 (its butterflies) + 8 (u sigma |g|_2 + u |x'|_2)
+//                                     (the two roundings of x'), |x'|_2 <= S (1 + u)
+//   channel estimate: + 32 u S for the reference's rounding of A + B, + 16 u S for fl(X~_A + X~_B), fl(N~_A + N~_B)
+//   => within (272 + 8 + 8 + 97 + 16 + 32 + 16) u S = 449 u S <= kRadius S = 512 u S.
+// A window's radius is therefore  kRadius |x|_2 + sigma kRadius |g|_2:  two norms per window per frame, one multiply-add
+// per SNR point.  kArithFast keeps only the EVM guard (bins with a tiny channel estimate are replayed exactly).
+#pragma once
+#include "ofdm_chain.cuh"
+
+namespace ofdm {
+
+struct SweepParams {
+    const float2 *in;               // TX frames [n_frames][320]
+    const float *g;                 // injected standard normals [n_frames][320]
+    const float *power;             // per-frame mean power (OFDM.c:637-643)
+    const uint32_t *tx_bits;        // [n_frames][6]
+    long n_frames;
+    int n_snr;
+    float radius_scale;             // kRadius, or infinity: every (frame, SNR point) is replayed exactly
+    float snr_lin[kMaxSnr];         // (float)pow(10, snr/10), OFDM.c:645
+    ofdm_counters *counters;        // [n_snr], accumulated into
+};
+
+struct alignas(16) SweepWarp {
+    float2 tile[kWarpTile];         // transform transpose tile
+    float2 fx[4][kWin];             // FFT of the clean windows: LTS half 1, LTS half 2, symbol 0, symbol 1 (natural bins)
+    float2 fn[4][kWin];             // FFT of the draws of the same windows
+    StreamStage<true> st[kStages];  // TMA ring: IQ windows + draw windows
+    uint64_t bar[kStages];
+    float norm[8];                  // kRadius |x_w|_2 (w = 0..3), kRadius |g_w|_2 (w = 0..3)
+};
+static_assert(sizeof(SweepWarp) % 16 == 0 && offsetof(SweepWarp, st) % 16 == 0 && offsetof(SweepWarp, norm) % 16 == 0, "SweepWarp alignment");
+
+template <int ARITH>
+__global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
+{
+    constexpr int LEVEL = ARITH == kArithChecked ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);                  // same value, provably warp-uniform
+    SweepWarp &ws = reinterpret_cast<SweepWarp *>(s_raw)[warp];
+    SweepWarp &ws_u = reinterpret_cast<SweepWarp *>(s_raw)[warp_u];
+    float2 *tile = ws.tile + grp * kGroupPitch;
+    Tw<false> tw; tw.load(u);
+    const ItemConst ic = make_items(lane);
+    const float k4[3] = {4.f * ic.sc[0], 4.f * ic.sc[1], 4.f * ic.sc[2]};     // 1 / sc
+    constexpr int len = 320;
+    const long stride = (long)gridDim.x * kWarpsPerBlock;
+    const long f_first = (long)blockIdx.x * kWarpsPerBlock + warp_u;
+    const double q = (double)kQpsk;
+    const double ref2_frame = 96.0 * (2.0 * q * q);
+    const float inv_ref2 = (float)(1.0 / ref2_frame);
+    constexpr uint32_t kBytes = 4 * 512 + 4 * 256;
+
+    const uint32_t stage0 = tma::saddr(&ws_u.st[0]);
+    const uint32_t bar0 = tma::saddr(&ws_u.bar[0]);
+    auto issue = [&](long f, int s) {          // f, s warp-uniform; whole warp calls (see k_stream_rx2)
+        if (tma::elect_one()) {
+            const uint32_t bar = bar0 + 8u * (uint32_t)s;
+            const uint32_t dst = stage0 + (uint32_t)s * (uint32_t)sizeof(StreamStage<true>);
+            const char *x = reinterpret_cast<const char *>(p.in) + f * (len * 8);
+            const char *g = reinterpret_cast<const char *>(p.g) + f * (len * 4);
+            const uint32_t gd = dst + 4 * kWin * 8;
+            tma::expect_tx_addr(bar, kBytes);
+            tma::bulk_addr(dst + 0 * kWin * 8, x + 32 * 8, 512, bar);             // Channel_Estimation :837
+            tma::bulk_addr(dst + 1 * kWin * 8, x + 96 * 8, 512, bar);             //                    :838
+            tma::bulk_addr(dst + 2 * kWin * 8, x + 176 * 8, 512, bar);            // CP strip :1028, symbol 0
+            tma::bulk_addr(dst + 3 * kWin * 8, x + 256 * 8, 512, bar);            //                 symbol 1
+            tma::bulk_addr(gd + 0 * kWin * 4, g + 32 * 4, 256, bar);
+            tma::bulk_addr(gd + 1 * kWin * 4, g + 96 * 4, 256, bar);
+            tma::bulk_addr(gd + 2 * kWin * 4, g + 176 * 4, 256, bar);
+            tma::bulk_addr(gd + 3 * kWin * 4, g + 256 * 4, 256, bar);
+        }
+    };
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) tma::mbar_init(&ws.bar[s], 1);
+        tma::fence_mbar_init();
+    }
+    __syncwarp();
+    for (int s = 0; s < kStages; ++s)
+        if (f_first + s * stride < p.n_frames) issue(f_first + s * stride, s);
+
+    // Per-SNR totals live in registers: lane L owns SNR points L and L + 32 (n_snr <= 64).  The float EVM sums are
+    // flushed into doubles every 64 frames.
+    uint32_t m_i[2] = {0, 0}, m_q[2] = {0, 0}, m_b[2] = {0, 0}, m_ferr[2] = {0, 0};
+    float m_e2[2] = {0.f, 0.f}, m_evm[2] = {0.f, 0.f};
+    double d_e2[2] = {0.0, 0.0}, d_evm[2] = {0.0, 0.0};
+    uint32_t n_done = 0;
+    uint32_t k = 0;                                   // frames this warp has consumed (ring position)
+    for (long f = f_first; f < p.n_frames; f += stride, ++k) {
+        const int s = (int)(k & 1u);
+        const uint32_t phase = (k >> 1) & 1u;
+        const float P = p.power[f];
+        const uint32_t *wb = p.tx_bits + f * 6;
+        uint32_t txp[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) txp[t] = wb[ic.word[t]] >> ic.shift[t];
+        // the noise scale of every SNR point, (float)sqrt((double)(P / snr)) (:647, :651), one (two) per lane
+        float sig_lo = 0.f, sig_hi = 0.f;
+        if (lane < p.n_snr) sig_lo = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane])));
+        if (lane + 32 < p.n_snr) sig_hi = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane + 32])));
+
+        tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
+        float2 v[8];
+        float gz[8];
+        float2 n2x = make_float2(0.f, 0.f);
+        float n2g = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = ws.st[s].x[grp][u + 8 * i];
+            gz[i] = ws.st[s].g[grp][u + 8 * i];
+            n2x = __ffma2_rn(v[i], v[i], n2x);
+            n2g = fmaf(gz[i], gz[i], n2g);
+        }
+        __syncwarp();                                         // every lane has its samples: the stage can be refilled
+        if (f + kStages * stride < p.n_frames) issue(f + kStages * stride, s);
+        fft64<false>(v, tw, tile, u);                         // X = FFT(x window)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ws.fx[grp][u + 8 * j] = v[j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = make_float2(gz[i], 0.f);     // the noise is real-rail only
+        fft64<false>(v, tw, tile, u);                         // N = FFT(g window)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ws.fn[grp][u + 8 * j] = v[j];
+        // window norms |x_w|_2, |g_w|_2 over the group's 8 lanes -> error radii per unit of (1, sigma)
+        float2 nn = make_float2(n2x.x + n2x.y, n2g);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1)
+            nn = __fadd2_rn(nn, make_float2(__shfl_xor_sync(0xffffffffu, nn.x, o), __shfl_xor_sync(0xffffffffu, nn.y, o)));
+        {
+            float rx, rn;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(nn.x));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nn.y));
+            const bool ok = nn.x >= 1e-30f && nn.x < 1e20f && nn.y < 1e20f;      // NaN fails; all-zero draws are fine
+            const float inf = __int_as_float(0x7f800000);
+            if (u == 0) { ws.norm[grp] = ok ? p.radius_scale * rx : inf; ws.norm[4 + grp] = ok ? p.radius_scale * rn : inf; }
+        }
+        __syncwarp();
+        // the lane's three data bins: everything the SNR loop needs, in registers
+        const float4 rX = *reinterpret_cast<const float4 *>(ws.norm), rN = *reinterpret_cast<const float4 *>(ws.norm + 4);
+        const float rHX = rX.x + rX.y, rHN = rN.x + rN.y;                      // 2 r_H = r_A + r_B
+        float2 FX[3], FN[3], GX[3], GN[3];
+        float rFX[3], rFN[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int bin = ic.bin[t];
+            GX[t] = cadd(ws.fx[0][bin], ws.fx[1][bin]);                        // A + B (:848), clean part
+            GN[t] = cadd(ws.fn[0][bin], ws.fn[1][bin]);                        //               noise part
+            FX[t] = (&ws.fx[2][0])[ic.f_off[t]];
+            FN[t] = (&ws.fn[2][0])[ic.f_off[t]];
+            const bool sym0 = t == 0 || (t == 1 && lane < 16);                 // items 0..47 belong to symbol 0
+            rFX[t] = sym0 ? rX.z : rX.w;
+            rFN[t] = sym0 ? rN.z : rN.w;
+        }
+        __syncwarp();                                         // everyone holds its items: fx / fn may be overwritten
+
+        // ---- SNR loop OFDM.c:1202: one packed multiply-add per value, then the decision stage.  Per-point results
+        // {packed rail errors, sum |e|^2} go through 64 words of shared memory (the noise tiles are free by now and the
+        // replay does not touch them) so that the owner lanes book them once per frame instead of branching per point.
+        uint2 *res = reinterpret_cast<uint2 *>(&ws.fn[0][0]);
+        for (int si = 0; si < p.n_snr; ++si) {
+            const float sg = __shfl_sync(0xffffffffu, si < 32 ? sig_lo : sig_hi, si & 31);
+            const float2 sg2 = make_float2(sg, sg);
+            const float rH2 = fmaf(sg, rHN, rHX);
+            const float gd = kEvmGuard * rH2, den_min4 = gd * gd;
+            float2 e2v = make_float2(0.f, 0.f);
+            uint32_t pk = 0;
+            bool doubt = false;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const float2 F = __ffma2_rn(sg2, FN[t], FX[t]);
+                const float2 G = __ffma2_rn(sg2, GN[t], GX[t]);
+                const float rF = fmaf(sg, rFN[t], rFX[t]);
+                pk += process_bin_spec<LEVEL>(F, G, k4[t], txp[t], rF, rH2, den_min4, e2v, doubt);
+            }
+            float e2 = e2v.x + e2v.y;
+            if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions / EVM: replay exactly
+                const double sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si]));
+                const uint2 r = stream_frame_replay<kNoiseInject>(p.in + f * len, p.g + f * len, wb, sigma_d, 0u, 0u, 0ull,
+                                                                  ws.tile, &ws.fx[0][0]);
+                pk = r.x; e2 = __uint_as_float(r.y);
+            }
+            pk = __reduce_add_sync(0xffffffffu, pk);                // one REDUX: the three 8-bit fields stay below 97
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+            if (lane == 0) res[si] = make_uint2(pk, __float_as_uint(e2));      // booked once per frame, below
+        }
+        __syncwarp();
+        // the lane that owns an SNR point books the frame's result for it (lanes beyond n_snr read stale words and add nothing)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint2 r = res[lane + 32 * h];
+            const bool mine = lane + 32 * h < p.n_snr;
+            const uint32_t pk = mine ? r.x : 0u;
+            const float e2 = mine ? __uint_as_float(r.y) : 0.f;
+            float evm;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(evm) : "f"(e2 * inv_ref2));                 // :1124
+            m_i[h] += pk & 0xFFu; m_q[h] += (pk >> 8) & 0xFFu; m_b[h] += pk >> 16; m_ferr[h] += pk != 0u;
+            m_e2[h] += e2; m_evm[h] += evm;
+        }
+        n_done += 1;
+        if ((n_done & 63u) == 0u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { d_e2[h] += (double)m_e2[h]; d_evm[h] += (double)m_evm[h]; m_e2[h] = 0.f; m_evm[h] = 0.f; }
+        }
+    }
+    if (n_done == 0) return;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int si = lane + 32 * h;
+        if (si >= p.n_snr) continue;
+        ofdm_counters *o = p.counters + si;
+        const unsigned long long ti = m_i[h], tq = m_q[h], tb = m_b[h];
+        atomicAdd(reinterpret_cast<unsigned long long *>(&o->bit_errors), ti + 2ull * tq - 2ull * tb);     // map of :423-430
+        atomicAdd(reinterpret_cast<unsigned long long *>(&o->rail_errors), ti + tq);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames_in_error), (unsigned long long)m_ferr[h]);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&o->frames), (unsigned long long)n_done);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&o->bits), 192ull * n_done);
+        atomicAdd(&o->sum_err2, d_e2[h] + (double)m_e2[h]);
+        atomicAdd(&o->sum_ref2, ref2_frame * (double)n_done);
+        atomicAdd(&o->sum_evm_lin, d_evm[h] + (double)m_evm[h]);
+    }
+}
+
+inline size_t sweep_smem_bytes() { return sizeof(SweepWarp) * kWarpsPerBlock; }
+
+}  // namespace ofdm

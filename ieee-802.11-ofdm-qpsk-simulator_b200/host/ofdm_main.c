@@ -16,6 +16,14 @@
  *       then the stage chain), OFDM.c:467-618 and :941-1165; --stage-chain keeps only the stage chain;
  *   --frames N (N > 1): N frames of Philox random bits per SNR point through the fused Monte-Carlo kernel.
  *   --taps L (with --frames N): configs[4], per-frame random multipath channel with L <= 16 taps in front of the noise;
+ *   --target-errors E [--max-bits B] [--round-frames R]: configs[3] as BASELINE.json states it -- every SNR point runs until it
+ *       has >= E bit errors or >= B bits (default B = E / 1e-7: the BER-1e-7 budget), in rounds of R frames (default 4 Mi);
+ *       finished points leave the kernel's SNR list, the others keep their noise streams.  With --gpus N every round's frame
+ *       range is split across the GPUs (so the slow high-SNR points use all of them) and the round's counters are all-reduced
+ *       (NCCL) before the stop decisions: the result does not depend on the GPU count;
+ *   --draws FILE [--bits FILE]: configs[1] from C -- injected-noise sweep (ofdm_sweep_inject_host): FILE holds one float32
+ *       standard-normal draw per sample, [frames][160 + 80 nsym] (e.g. the reference's captured g_keep stream); the payload is
+ *       the Philox bit stream of --seed, or packed uint32 words [frames][3 nsym] from --bits;
  *   --gpus N: the frames of the Monte-Carlo sweep are sharded across N GPUs of this node by global frame index
  *       (one context per GPU, all driven from this thread) and the counters are summed with ONE NCCL all-reduce
  *       per buffer type (built with -DOFDM_WITH_NCCL; link -lnccl).
@@ -95,7 +103,8 @@ static void report_rate(const char *what, int n_gpus, long frames, int n_sym, in
     } while (0)
 
 /* shard (frame range) across GPUs, counter-based RNG keyed on the global frame index, one all-reduce */
-static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, int n_taps, const float *SNR, int n_snr, int mode, ofdm_counters *totals)
+static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, int n_taps, const float *SNR, int n_snr, int mode, ofdm_counters *totals,
+                           unsigned long long target_errors, unsigned long long max_bits, long round_frames)
 {
     ofdm_ctx *ctxs[8] = {0};
     ofdm_ctx *ctx = NULL;
@@ -119,6 +128,59 @@ static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, in
         else CHECK(ofdm_mc_sweep_philox_dev(ctx, seed, 0, 256, n_sym, SNR, n_snr, mode, (ofdm_counters *)cnt[d]));
         CHECK(ofdm_memset_dev(ctx, cnt[d], 0, sizeof(ofdm_counters) * (size_t)n_snr));
         CHECK(ofdm_ctx_sync(ctx));
+    }
+    if (target_errors > 0) {
+        /* configs[3]'s stop rule, sharded as (SNR point x frame range): every GPU works on every still-active point, on its
+         * slice of the round's frames; one all-reduce per buffer type per round; identical stop decisions everywhere */
+        int active[64], n_active = n_snr, rounds = 0;
+        unsigned long long done_frames = 0;
+        ofdm_counters part[64];
+        memset(totals, 0, sizeof(ofdm_counters) * (size_t)n_snr);
+        for (int i = 0; i < n_snr; ++i) active[i] = i;
+        const double t0 = now_s();
+        while (n_active > 0) {
+            float snr_a[64]; uint32_t stream_a[64];
+            for (int j = 0; j < n_active; ++j) { snr_a[j] = SNR[active[j]]; stream_a[j] = (uint32_t)active[j]; }
+            for (int d = 0; d < n_gpus; ++d) {
+                long base = round_frames / n_gpus, rem = round_frames % n_gpus;
+                long lo = d * base + (d < rem ? d : rem), n = base + (d < rem ? 1 : 0);
+                ctx = ctxs[d];
+                CHECK(ofdm_memset_dev(ctx, cnt[d], 0, sizeof(ofdm_counters) * (size_t)n_active));
+                CHECK(ofdm_mc_sweep_points_dev(ctx, seed, (uint64_t)rounds * (uint64_t)round_frames + (uint64_t)lo, n, n_sym, n_taps, snr_a, stream_a,
+                                               n_active, mode, (ofdm_counters *)cnt[d]));
+                CHECK(ofdm_counters_pack(ctx, (const ofdm_counters *)cnt[d], n_active, (uint64_t *)ints[d], (double *)dbls[d]));
+            }
+            NCHECK(ncclGroupStart());
+            for (int d = 0; d < n_gpus; ++d) {
+                NCHECK(ncclAllReduce(ints[d], ints[d], 5 * (size_t)n_active, ncclUint64, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+                NCHECK(ncclAllReduce(dbls[d], dbls[d], 3 * (size_t)n_active, ncclDouble, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+            }
+            NCHECK(ncclGroupEnd());
+            ctx = ctxs[0];
+            CHECK(ofdm_counters_unpack(ctx, (ofdm_counters *)cnt[0], n_active, (const uint64_t *)ints[0], (const double *)dbls[0]));
+            CHECK(ofdm_memcpy_d2h(ctx, part, cnt[0], sizeof(ofdm_counters) * (size_t)n_active));
+            for (int d = 0; d < n_gpus; ++d) { ctx = ctxs[d]; CHECK(ofdm_ctx_sync(ctx)); }
+            int keep = 0;
+            for (int j = 0; j < n_active; ++j) {
+                ofdm_counters *t = &totals[active[j]];
+                t->bit_errors += part[j].bit_errors; t->bits += part[j].bits; t->frames_in_error += part[j].frames_in_error;
+                t->rail_errors += part[j].rail_errors; t->frames += part[j].frames;
+                t->sum_err2 += part[j].sum_err2; t->sum_ref2 += part[j].sum_ref2; t->sum_evm_lin += part[j].sum_evm_lin;
+                done_frames += part[j].frames;
+                if (t->bit_errors < target_errors && t->bits < max_bits) active[keep++] = active[j];
+            }
+            n_active = keep;
+            ++rounds;
+        }
+        const double dt = now_s() - t0;
+        fprintf(stderr, "until-sweep: %d rounds of %ld frames, %llu frame-points x %d symbols on %d GPU(s) in %.3f s = %.3e data symbols/s\n", rounds,
+                round_frames, done_frames, n_sym, n_gpus, dt, (double)done_frames * n_sym / dt);
+        for (int d = 0; d < n_gpus; ++d) {
+            ncclCommDestroy(comms[d]);
+            ofdm_dev_free(ctxs[d], cnt[d]); ofdm_dev_free(ctxs[d], ints[d]); ofdm_dev_free(ctxs[d], dbls[d]);
+            ofdm_ctx_destroy(ctxs[d]);
+        }
+        return 0;
     }
     const double t0 = now_s();
     for (int d = 0; d < n_gpus; ++d) {                      /* all GPUs run their shard concurrently (async launches) */
@@ -160,6 +222,9 @@ int main(int argc, char **argv)
     int n_sym = 2, n_snr = 35, device = 0, mode = OFDM_MODE_EXACT, quiet = 0, n_gpus = 1, full_chain = 1, n_taps = 0;
     float snr_start = 6.0f, snr_step = 1.0f;             /* OFDM.c:18, :1195-1198 */
     unsigned seed = 1;
+    unsigned long long target_errors = 0, max_bits = 0;
+    long round_frames = 1L << 22;
+    const char *draws_file = NULL, *bits_file = NULL;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
         if (!strcmp(a, "--quiet")) { quiet = 1; continue; }
@@ -176,6 +241,11 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "--device")) device = atoi(v);
         else if (!strcmp(a, "--gpus")) n_gpus = atoi(v);
         else if (!strcmp(a, "--taps")) n_taps = atoi(v);
+        else if (!strcmp(a, "--target-errors")) target_errors = strtoull(v, NULL, 10);
+        else if (!strcmp(a, "--max-bits")) max_bits = strtoull(v, NULL, 10);
+        else if (!strcmp(a, "--round-frames")) round_frames = atol(v);
+        else if (!strcmp(a, "--draws")) draws_file = v;
+        else if (!strcmp(a, "--bits")) bits_file = v;
         else if (!strcmp(a, "--outdir")) outdir = v;
         else if (!strcmp(a, "--dump")) dump = v;
         else if (!strcmp(a, "--mode")) mode = !strcmp(v, "fast") ? OFDM_MODE_FAST : OFDM_MODE_EXACT;
@@ -183,6 +253,8 @@ int main(int argc, char **argv)
         ++i;
     }
     if (n_snr < 1 || n_snr > 64 || frames < 1) { fprintf(stderr, "need 1 <= snr-count <= 64 and frames >= 1\n"); return 2; }
+    if (target_errors > 0 && max_bits == 0) max_bits = target_errors * 10000000ULL;        /* the BER-1e-7 budget */
+    if (round_frames < 1) { fprintf(stderr, "--round-frames must be >= 1\n"); return 2; }
 
     ofdm_ctx *ctx = NULL;
     float SNR[64], EVM_dB[64], EVM_AGC_dB[64], BER[64];
@@ -191,8 +263,8 @@ int main(int argc, char **argv)
 
     if (n_gpus > 1) {
 #ifdef OFDM_WITH_NCCL
-        if (frames < 2) { fprintf(stderr, "--gpus needs --frames N > 1\n"); return 2; }
-        int rc = sweep_multi_gpu(n_gpus, seed, frames, n_sym, n_taps, SNR, n_snr, mode, totals);
+        if (frames < 2 && target_errors == 0) { fprintf(stderr, "--gpus needs --frames N > 1 or --target-errors E\n"); return 2; }
+        int rc = sweep_multi_gpu(n_gpus, seed, frames, n_sym, n_taps, SNR, n_snr, mode, totals, target_errors, max_bits, round_frames);
         if (rc) return rc;
 #else
         fprintf(stderr, "built without NCCL (make ofdm_sweep NCCL=1)\n");
@@ -203,6 +275,46 @@ int main(int argc, char **argv)
 
     if (n_gpus > 1) {
         /* totals already hold the all-reduced counters */
+    } else if (draws_file) {                           /* configs[1]: injected-noise sweep from host buffers */
+        const int len = OFDM_FRAME_LEN(n_sym);
+        FILE *fd = fopen(draws_file, "rb");
+        if (!fd) { perror(draws_file); return 1; }
+        fseek(fd, 0, SEEK_END);
+        const long n_avail = ftell(fd) / ((long)len * 4);
+        fseek(fd, 0, SEEK_SET);
+        if (frames <= 1 || frames > n_avail) frames = n_avail;
+        if (frames < 1) { fprintf(stderr, "%s: shorter than one frame of draws (%d floats)\n", draws_file, len); return 1; }
+        void *g_host = NULL, *b_host = NULL;
+        CHECK(ofdm_host_alloc(ctx, &g_host, (size_t)frames * len * 4));
+        CHECK(ofdm_host_alloc(ctx, &b_host, (size_t)frames * n_sym * 12));
+        if (fread(g_host, (size_t)len * 4, (size_t)frames, fd) != (size_t)frames) { fprintf(stderr, "%s: short read\n", draws_file); return 1; }
+        fclose(fd);
+        if (bits_file) {
+            FILE *fb = fopen(bits_file, "rb");
+            if (!fb) { perror(bits_file); return 1; }
+            if (fread(b_host, (size_t)n_sym * 12, (size_t)frames, fb) != (size_t)frames) { fprintf(stderr, "%s: short read\n", bits_file); return 1; }
+            fclose(fb);
+        } else {                                       /* the Philox bit stream of --seed (frame index = position in the file) */
+            void *d_b = NULL;
+            CHECK(ofdm_dev_alloc(ctx, &d_b, (size_t)frames * n_sym * 12));
+            CHECK(ofdm_random_bits(ctx, seed, 0, frames, n_sym, (uint32_t *)d_b));
+            CHECK(ofdm_memcpy_d2h(ctx, b_host, d_b, (size_t)frames * n_sym * 12));
+            CHECK(ofdm_ctx_sync(ctx));
+            ofdm_dev_free(ctx, d_b);
+        }
+        const double t0 = now_s();
+        CHECK(ofdm_sweep_inject_host(ctx, (const uint32_t *)b_host, (const float *)g_host, frames, n_sym, SNR, n_snr, mode, totals));
+        report_rate("injected-noise sweep (host buffers)", 1, frames, n_sym, n_snr, now_s() - t0);
+        ofdm_host_free(ctx, g_host); ofdm_host_free(ctx, b_host);
+    } else if (target_errors > 0) {                    /* configs[3]: until >= E errors or the bit budget, one GPU */
+        int rounds = 0;
+        const double t0 = now_s();
+        CHECK(ofdm_mc_sweep_until(ctx, seed, 0, n_sym, n_taps, SNR, n_snr, mode, target_errors, max_bits, round_frames, totals, &rounds));
+        unsigned long long fp = 0;
+        for (int i = 0; i < n_snr; ++i) fp += totals[i].frames;
+        const double dt = now_s() - t0;
+        fprintf(stderr, "until-sweep: %d rounds of %ld frames, %llu frame-points x %d symbols on 1 GPU(s) in %.3f s = %.3e data symbols/s\n", rounds, round_frames,
+                fp, n_sym, dt, (double)fp * n_sym / dt);
     } else if (frames > 1 && n_taps > 0) {             /* configs[4]: per-frame random multipath taps */
         void *d_cnt = NULL;
         CHECK(ofdm_dev_alloc(ctx, &d_cnt, sizeof(ofdm_counters) * (size_t)n_snr));

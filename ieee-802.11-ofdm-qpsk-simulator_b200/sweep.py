@@ -77,6 +77,54 @@ def mc_sweep_sharded(ofdm, seed, n_frames_total, n_sym, snr_db, mode, rank=0, wo
     return ofdm.read_counters(cnt)
 
 
+def until_loop(run_round, n_points, target_errors, max_bits, round_frames, rank=0, world=1, allreduce=None, frame0=0, max_rounds=None):
+    """The stop rule of configs[3] over any number of ranks: every point runs until it has >= target_errors bit errors or
+    >= max_bits bits.  Round r covers the global frames [frame0 + r * round_frames, + round_frames), split across the ranks
+    by shard_range; ``run_round(points, lo, n)`` returns this rank's (int64 [len(points), 5], float64 [len(points), 3]) totals
+    for the points still active on frames [lo, lo + n); ``allreduce(ints, dbls)`` sums them over the ranks (None: single
+    rank).  Stop decisions are taken on the all-reduced totals at round boundaries, so every rank takes the same decisions
+    and the result is the single-rank result (ofdm_mc_sweep_until) whatever the world size.  Returns (ints, dbls, rounds)."""
+    ints = np.zeros((n_points, N_INT_FIELDS), np.int64)
+    dbls = np.zeros((n_points, 3), np.float64)
+    active = list(range(n_points))
+    rounds = 0
+    while active and (max_rounds is None or rounds < max_rounds):
+        lo, hi = shard_range(round_frames, rank, world)
+        pi, pd = run_round(active, frame0 + rounds * round_frames + lo, hi - lo)
+        pi, pd = np.array(pi, dtype=np.int64).reshape(len(active), N_INT_FIELDS), np.array(pd, dtype=np.float64).reshape(len(active), 3)
+        if allreduce is not None and world > 1:
+            pi, pd = allreduce(pi, pd)
+        ints[active] += pi
+        dbls[active] += pd
+        active = [i for i in active if ints[i, 0] < target_errors and ints[i, 1] < max_bits]
+        rounds += 1
+    return ints, dbls, rounds
+
+
+def mc_sweep_until(ofdm, seed, n_sym, snr_db, mode, target_errors=100, max_bits=10 ** 9, round_frames=1 << 22, n_taps=0, rank=0, world=1,
+                   group=None, frame0=0):
+    """configs[3] as stated, on ``world`` GPUs: SNR points x frame ranges are sharded by rounds (every rank works on every
+    still-active point, on its own slice of the round's frames -- so the slow high-SNR points use all GPUs), one all-reduce
+    of the counters per round.  Returns (list of global Counters, rounds) on every rank."""
+    import torch
+    import torch.distributed as dist
+    snr = np.asarray(snr_db, dtype=np.float32)
+    cnt = ofdm.new_counters(len(snr))
+
+    def run_round(points, lo, n):
+        c = cnt[:len(points)]
+        c.zero_()
+        if n > 0:
+            ofdm.mc_sweep_points(seed, lo, n, n_sym, n_taps, snr[points], np.asarray(points, dtype=np.uint32), mode, c)
+        if world > 1:
+            allreduce_counter_tensor(c, group)              # on the device: NCCL over NVLink
+        raw = c.cpu().numpy()
+        return raw[:, :N_INT_FIELDS].copy(), raw[:, N_INT_FIELDS:].copy().view(np.float64)
+
+    ints, dbls, rounds = until_loop(run_round, len(snr), target_errors, max_bits, round_frames, rank, world, None, frame0)
+    return arrays_to_counters(ints, dbls), rounds
+
+
 def ber_table(snr_db, counters):
     rows = []
     for s, c in zip(snr_db, counters):

@@ -102,6 +102,8 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *                            both give the same error counts)
  *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path)
  *   "general_stream"    = 1  two-symbol frames also take the multi-pass streaming kernel that serves every other frame shape
+ *   "fused_sweep"       = 0  injected-noise sweeps launch one channel+receiver kernel per SNR point instead of the all-SNR
+ *                            kernel (default 1; same totals)
  *   "multipath_path"    = 0  ofdm_mc_sweep_multipath_dev picks the faster of its two implementations per mode (default);
  *                       = 1  frames staged in HBM (TX, fading, power, one receiver kernel per SNR point);
  *                       = 2  the fused on-chip kernel; both give the same totals */
@@ -161,6 +163,34 @@ int ofdm_awgn_rx_philox(ofdm_ctx *ctx, const float *tx_dev, const float *power_d
                         float snr_db, uint32_t seed, uint32_t stream, uint64_t frame0, long n_frames, int n_sym,
                         int mode, ofdm_counters *counters_dev, const ofdm_rx_dump *dump);
 
+/* the same over a list of SNR points (device buffers, counters_dev [n_snr] accumulated into, no synchronisation): for
+ * two-symbol frames this is ONE kernel for the whole list (k_sweep_lin: the transform is linear, so each frame and its
+ * draws are transformed once and every SNR point costs a multiply-add per bin plus the decision stage; EXACT mode keeps
+ * the reference's error counts by verification + exact replay); other shapes launch per point. */
+int ofdm_awgn_rx_inject_sweep(ofdm_ctx *ctx, const float *tx_dev, const float *g_dev, const float *power_dev,
+                              const uint32_t *tx_bits_dev, const float *snr_db, int n_snr, long n_frames, int n_sym, int mode,
+                              ofdm_counters *counters_dev);
+
+/* ---- the receiver's stages one by one (device buffers; what ofdm_rx_frames fuses) ------------------------------------
+ * 1:1 batched counterparts of the reference's receiver functions and inline blocks, so that a caller can stop after any
+ * stage exactly as with the reference.  Chained -- strip_cp, fft64, channel_estimate, equalize, demap, agc_slicer,
+ * qpsk_demodulate -- they reproduce the reference's H_est, equalised points, slicer output and bits bit for bit in EXACT mode.
+ * ofdm_strip_cp         CP strip, OFDM.c:1024-1031: frames [n][frame_len] -> bodies [n][n_sym][64]; data_off = index of the
+ *                       first data symbol's CP (160 for LTS || data frames, 320 for the reference's STS || LTS || data frame)
+ * ofdm_channel_estimate Channel_Estimation, OFDM.c:830-850: H [n][64] centred = 0.5 (fft(LTS half 1) + fft(LTS half 2)) conj(L);
+ *                       lts_off = index of the LTS slot (0, or 160 behind an STS slot: the reference reads samples 192..319)
+ * ofdm_equalize         one-tap ZF, OFDM.c:1044-1052: E [n][n_sym][64] = F / H on all 64 bins (libgcc __divsc3 in EXACT mode;
+ *                       the 12 null bins hold the inf / NaN the reference computes there and never reads)
+ * ofdm_demap            OFDM.c:1059-1069: [n_symbols][64] -> the 48 data bins [n_symbols][48]
+ * ofdm_agc_slicer       AGC_Receiver, OFDM.c:852-871: each rail -> +1/sqrt(2) if > 0 else -1/sqrt(2)
+ * ofdm_qpsk_demodulate  QPSK_Demodulator, OFDM.c:873-908: [n_symbols][48] points -> packed bits [n_symbols][3] */
+int ofdm_strip_cp(ofdm_ctx *ctx, const float *frames_dev, float *bodies_dev, long n_frames, int n_sym, int frame_len, int data_off);
+int ofdm_channel_estimate(ofdm_ctx *ctx, const float *frames_dev, float *H_dev, long n_frames, int frame_len, int lts_off, int mode);
+int ofdm_equalize(ofdm_ctx *ctx, const float *F_dev, const float *H_dev, float *E_dev, long n_frames, int n_sym, int mode);
+int ofdm_demap(ofdm_ctx *ctx, const float *grid_dev, float *points_dev, long n_symbols);
+int ofdm_agc_slicer(ofdm_ctx *ctx, const float *points_dev, float *sliced_dev, long n_symbols);
+int ofdm_qpsk_demodulate(ofdm_ctx *ctx, const float *points_dev, uint32_t *bits_dev, long n_symbols);
+
 /* ---- sweep drivers: host buffers in, host counters out (what main()'s loop OFDM.c:1202-1222 does) ---- */
 /* Transmitter once, then per SNR point channel + receiver, injected normals reused across points
  * (only the scale changes).  bits_host [n_frames][n_sym*3] packed; g_host [n_frames][frame_len];
@@ -184,6 +214,21 @@ int ofdm_mc_sweep_philox_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long
 int ofdm_mc_sweep_philox(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym,
                          const float *snr_db, int n_snr, int mode, ofdm_counters *out_host);
 
+/* The same over an explicit list of points: streams[i] (NULL: i) is the Philox noise stream of point i, so that a caller
+ * can drop finished SNR points from the list without changing the draws of the others; n_taps = 0 is the AWGN channel,
+ * 1..16 the multipath channel of configs[4] below.  n_points <= 64.  Accumulates into counters_dev, no synchronisation. */
+int ofdm_mc_sweep_points_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, int n_sym, int n_taps,
+                             const float *snr_db, const uint32_t *streams, int n_points, int mode, ofdm_counters *counters_dev);
+/* configs[3] as BASELINE.json states it: every SNR point runs until it has >= target_errors bit errors or >= max_bits
+ * bits (the BER budget: 100 errors / 1e-7 = 1e9 bits), whichever comes first.  Frames are consumed in rounds of round_frames
+ * (global frame indices frame0 + r * round_frames ...); after a round the finished points leave the kernel's list.  The
+ * stop decisions are taken at round boundaries on totals, so the result depends only on (seed, frame0, round_frames): a
+ * multi-GPU driver that splits each round's frame range across ranks and all-reduces the round's counters before
+ * deciding reproduces it exactly (host/ofdm_main.c --target-errors; sweep.mc_sweep_until).  out_host [n_snr]; rounds_out nullable. */
+int ofdm_mc_sweep_until(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, int n_sym, int n_taps, const float *snr_db, int n_snr,
+                        int mode, uint64_t target_errors, uint64_t max_bits, long round_frames, ofdm_counters *out_host,
+                        int *rounds_out);
+
 /* ---- multipath extension (BASELINE configs[4]; the reference's only channel is AWGN, OFDM.c:635-655) ----
  * y[n] = sum_l h[l] x[n-l] per frame, n_taps <= 16 (= CP length), applied between the transmitter and
  * Transmission_Over_Air; the reference's own LTS estimate + one-tap equaliser (OFDM.c:830-850, 1046-1052) undo it.
@@ -203,7 +248,7 @@ int ofdm_mc_sweep_multipath_dev(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, l
  *   OFDM.c:342-364: [n_frames][frame_len] -> [n_frames][2*frame_len + 20].
  * ofdm_rrc_rx: matched filter + decimation, OFDM.c:959-996: full convolution of in_len samples, then every 2nd sample
  *   from packet_idx, frame_len of them.  packet_idx = 20 re-aligns a frame shaped by ofdm_rrc_tx (the reference finds
- *   it with Packet_Detection/Packet_Selection, which are not part of this library yet).
+ *   it with Packet_Detection/Packet_Selection: ofdm_packet_detect / ofdm_packet_select below, then ofdm_rrc_rx_idx).
  * ofdm_awgn_inject_len: Transmission_Over_Air (OFDM.c:635) on frames of any length, e.g. the oversampled waveform. */
 int ofdm_rrc_tx(ofdm_ctx *ctx, const float *frames_dev, float *out_dev, long n_frames, int frame_len);
 int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in_dev, float *out_dev, long n_frames, int in_len, int packet_idx, int frame_len);
