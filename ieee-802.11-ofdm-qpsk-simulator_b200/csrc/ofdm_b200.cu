@@ -603,7 +603,17 @@ int ofdm_tx_frames(ofdm_ctx *ctx, const uint32_t *bits, float *frames, float *po
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, bits != nullptr && frames != nullptr);
     int st;
-    if (mode == OFDM_MODE_EXACT) {
+    if (n_sym == 2 && (uintptr_t)frames % 16 == 0 && !ctx->force_generic) {
+        // default frame shape: frames leave shared memory through the TMA engine (k_tx_frames2)
+        const size_t smem = tx2_smem_bytes();
+        auto launch = [&](auto k) -> int {
+            OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = grid_for(ctx, k, smem, kWarpsPerBlock * 2, n_frames);
+            k<<<grid, kThreads, smem, ctx->stream>>>(bits, reinterpret_cast<float2 *>(frames), n_frames);
+            return check_launch(ctx, "k_tx_frames2");
+        };
+        st = mode == OFDM_MODE_EXACT ? launch(k_tx_frames2<true>) : launch(k_tx_frames2<false>);
+    } else if (mode == OFDM_MODE_EXACT) {
         int grid = grid_for(ctx, k_tx_frames<true>, 0, kWarpsPerBlock * 4, n_frames * n_sym);
         k_tx_frames<true><<<grid, kThreads, 0, ctx->stream>>>(bits, reinterpret_cast<float2 *>(frames), n_frames, n_sym);
         st = check_launch(ctx, "k_tx_frames<exact>");
@@ -1072,17 +1082,18 @@ static int multipath_common(ofdm_ctx *ctx, bool philox, const float *tx, const f
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, tx != nullptr && out != nullptr && tx != out && (philox || taps != nullptr));
     const int len = OFDM_FRAME_LEN(n_sym);
-    const size_t smem = (size_t)kWarpsPerBlock * (len + kMaxTaps) * sizeof(float2);
+    const int tile = fir_tile(len);
+    const size_t smem = fir_smem_bytes(tile);
     const float2 *x = reinterpret_cast<const float2 *>(tx), *h = reinterpret_cast<const float2 *>(taps);
     float2 *y = reinterpret_cast<float2 *>(out), *ho = reinterpret_cast<float2 *>(taps_out);
     if (philox) {
-        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
         int grid = grid_for(ctx, k_multipath<true>, smem, kWarpsPerBlock, n_frames);
-        k_multipath<true><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len);
+        k_multipath<true><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len, tile);
     } else {
-        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
         int grid = grid_for(ctx, k_multipath<false>, smem, kWarpsPerBlock, n_frames);
-        k_multipath<false><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len);
+        k_multipath<false><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len, tile);
     }
     return check_launch(ctx, "k_multipath");
 }
@@ -1179,10 +1190,11 @@ int ofdm_rrc_tx(ofdm_ctx *ctx, const float *frames, float *out, long n_frames, i
     OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= OFDM_FRAME_LEN(OFDM_MAX_SYM));
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, frames != nullptr && out != nullptr && frames != out);
-    const size_t smem = (size_t)kWarpsPerBlock * frame_len * sizeof(float2);
-    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_tx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tile = fir_tile(frame_len);
+    const size_t smem = fir_smem_bytes(tile);
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_tx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
     int grid = grid_for(ctx, k_rrc_tx, smem, kWarpsPerBlock, n_frames);
-    k_rrc_tx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), reinterpret_cast<float2 *>(out), n_frames, frame_len);
+    k_rrc_tx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), reinterpret_cast<float2 *>(out), n_frames, frame_len, tile);
     return check_launch(ctx, "k_rrc_tx");
 }
 int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in, float *out, long n_frames, int in_len, int packet_idx, int frame_len)
@@ -1193,18 +1205,19 @@ int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in, float *out, long n_frames, int i
     OFDM_REQUIRE(ctx, (long)packet_idx + 2L * (frame_len - 1) < (long)in_len + 20);
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && in != out);
-    const size_t smem = (size_t)kWarpsPerBlock * in_len * sizeof(float2);
-    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tile = fir_tile(2 * frame_len);
+    const size_t smem = fir_smem_bytes(tile);
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
     int grid = grid_for(ctx, k_rrc_rx, smem, kWarpsPerBlock, n_frames);
-    k_rrc_rx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), n_frames, in_len,
-                                                   packet_idx, frame_len);
+    k_rrc_rx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), nullptr, packet_idx, reinterpret_cast<float2 *>(out), n_frames,
+                                                   in_len, frame_len, tile);
     return check_launch(ctx, "k_rrc_rx");
 }
 int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx, const float *g, const float *power, float snr_db, float *ota, long n_frames,
                          int frame_len, int mode)
 {
     if (int st = bind(ctx)) return st;
-    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= 2 * OFDM_FRAME_LEN(OFDM_MAX_SYM) + 64 && mode_ok(mode));
+    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= (1 << 24) && mode_ok(mode));
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, tx != nullptr && ota != nullptr && g != nullptr);
     const float *pw = nullptr;
@@ -1226,13 +1239,15 @@ int ofdm_awgn_inject_len(ofdm_ctx *ctx, const float *tx, const float *g, const f
 int ofdm_packet_detect(ofdm_ctx *ctx, const float *rx, float *corr, long n, int len)
 {
     if (int st = bind(ctx)) return st;
-    OFDM_REQUIRE(ctx, n >= 0 && len >= 48 && len <= 12000);
+    OFDM_REQUIRE(ctx, n >= 0 && len >= 48);
     if (n == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, rx != nullptr && corr != nullptr);
-    const size_t smem = (size_t)len * (sizeof(double) + sizeof(float2));
-    OFDM_CUDA(ctx, cudaFuncSetAttribute(k_packet_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int tile = (len - 47 + 31) & ~31;
+    if (tile > 4096) tile = 4096;
+    const size_t smem = (size_t)(tile + 48) * (sizeof(double) + sizeof(float2));
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_packet_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((4096 + 48) * 16)));
     int grid = grid_for(ctx, k_packet_detect, smem, 1, n);                  // one capture per block iteration, all resident blocks
-    k_packet_detect<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(rx), corr, n, len);
+    k_packet_detect<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(rx), corr, n, len, tile);
     return check_launch(ctx, "k_packet_detect");
 }
 int ofdm_packet_select(ofdm_ctx *ctx, const float *corr, int32_t *idx, long n, int len_corr)
@@ -1278,14 +1293,15 @@ int ofdm_gather(ofdm_ctx *ctx, const float *in, const int32_t *start, int start_
 int ofdm_rrc_rx_idx(ofdm_ctx *ctx, const float *in, const int32_t *idx, float *out, long n_frames, int in_len, int frame_len)
 {
     if (int st = bind(ctx)) return st;
-    OFDM_REQUIRE(ctx, n_frames >= 0 && in_len >= 1 && in_len <= 12000 && frame_len >= 1);
+    OFDM_REQUIRE(ctx, n_frames >= 0 && in_len >= 1 && frame_len >= 1);
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && idx != nullptr && in != out);
-    const size_t smem = (size_t)kWarpsPerBlock * in_len * sizeof(float2);
-    OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx_idx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = grid_for(ctx, k_rrc_rx_idx, smem, kWarpsPerBlock, n_frames);
-    k_rrc_rx_idx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), idx, reinterpret_cast<float2 *>(out), n_frames, in_len, frame_len);
-    return check_launch(ctx, "k_rrc_rx_idx");
+    const int tile = fir_tile(2 * frame_len);
+    const size_t smem = fir_smem_bytes(tile);
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
+    int grid = grid_for(ctx, k_rrc_rx, smem, kWarpsPerBlock, n_frames);
+    k_rrc_rx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), idx, 0, reinterpret_cast<float2 *>(out), n_frames, in_len, frame_len, tile);
+    return check_launch(ctx, "k_rrc_rx(idx)");
 }
 static int cfo_common(ofdm_ctx *ctx, bool fine, const float *rx, float *out, float *freq, long n, int len)
 {
@@ -1311,7 +1327,7 @@ int ofdm_awgn_philox_len(ofdm_ctx *ctx, const float *tx, const float *power, flo
                          float *ota, long n_frames, int frame_len, int mode)
 {
     if (int st = bind(ctx)) return st;
-    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= 2 * OFDM_FRAME_LEN(OFDM_MAX_SYM) + 64 && mode_ok(mode));
+    OFDM_REQUIRE(ctx, n_frames >= 0 && frame_len >= 1 && frame_len <= (1 << 24) && mode_ok(mode));
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, tx != nullptr && ota != nullptr);
     const float *pw = nullptr;

@@ -27,13 +27,25 @@ struct ItemConst {
     int shift[3];                   // position of the pair in that word
 };
 
+// Which of the frame's 96 data bins a lane takes.  The exchange tiles are read with 64-bit loads, one half-warp (16 lanes) per
+// shared-memory wavefront: a load is conflict-free when the 16 lanes touch 16 different bank pairs (element index mod 16) or
+// the same address.  Dealing the data indices out in order (item t = lane + 32 r) cannot achieve that -- 16 consecutive data
+// bins span 17 or 18 FFT bins because of the pilot / DC gaps, so two of them always collide (18 extra wavefronts per frame).
+// Instead each half-warp takes 8 bins for BOTH symbols (lanes 0..7 symbol 0, lanes 8..15 symbol 1): the LTS tiles are then
+// read at 8 addresses, each by two lanes (a broadcast), and the symbol tiles sit 72 = 8 (mod 16) elements apart, so the bins
+// of a group only have to differ mod 8 -- which the table below (found by search, tools/deal_search.py) achieves for all
+// groups but one: 1 extra wavefront per frame instead of 18.  Row = 2 r + half-warp.
+__constant__ unsigned char c_deal_bin[48] = { 2, 10, 12, 14, 16, 23, 49, 54,    1,  3, 18, 40, 46, 60, 61, 63,   22, 25, 45, 47, 48, 50, 52, 59,
+                                              4,  6,  9, 11, 13, 24, 39, 58,    8, 41, 42, 44, 51, 53, 55, 62,    5, 15, 17, 19, 20, 26, 38, 56};
+
 __device__ __forceinline__ ItemConst make_items(int lane)
 {
     ItemConst c;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const int t = lane + 32 * r, sym = t / 48, d = t - 48 * sym;
-        const int bin = c_tab.data_bin[d];
+        const int sym = (lane >> 3) & 1;
+        const int bin = c_deal_bin[(2 * r + (lane >> 4)) * 8 + (lane & 7)];
+        const int d = c_tab.bin_data[bin];
         c.f_off[r] = sym * kWin + bin;
         c.bin[r] = bin;
         c.sc[r] = 0.5f * (float)c_tab.bin_lts[bin];
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 for (int t = 0; t < 3; ++t) {
                     const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
                     const float2 G = cadd(A, B);
-                    const float rF = t == 0 ? r0 : t == 2 ? r1 : (lane < 16 ? r0 : r1);
+                    const float rF = ic.f_off[t] < kWin ? r0 : r1;
                     pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], txp[t], rF, rH2, den_min4, e2v, doubt);
                 }
                 e2 = e2v.x + e2v.y;
@@ -560,6 +572,86 @@ __device__ __forceinline__ void wait(uint64_t *bar, uint32_t phase)
                  "}" ::"r"(saddr(bar)), "r"(phase) : "memory");
 }
 }  // namespace tma
+
+// ------------------------------------------------------------------------------------------------
+// k_tx_frames2 -- the transmitter for the default frame shape (LTS + 2 symbols), frames leaving through the TMA engine.
+// A warp builds two frames per pass (lane group 2 s + k = symbol s of frame k) in shared memory -- the LTS slot is a
+// constant of the build and is written into the frame images once, at kernel start -- and one elected lane hands each
+// finished 2560-byte frame image to a bulk async copy (cp.async.bulk.global.shared::cta, SASS UBLKCP): the SM issues two
+// store instructions per pair of frames instead of ~60 per lane, and HBM sees whole, aligned 2560-byte writes.  Two sets of
+// images alternate so that a pass can fill one while the copy engine drains the other (bulk_group / wait_group.read).
+// The image of the second frame sits 8 elements further (pitch 328) so that the two half-warp partners never hit the
+// same bank pair.
+constexpr int kTxPitch = 328;           // float2 per frame image: 320 + 8 of skew
+struct alignas(16) TxWarp { float2 img[2][2][kTxPitch]; };
+inline size_t tx2_smem_bytes() { return sizeof(TxWarp) * kWarpsPerBlock; }
+
+namespace tma {
+__device__ __forceinline__ void bulk_s2g(void *dst_global, uint32_t src_shared, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_shared), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace tma
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kThreads) k_tx_frames2(const uint32_t *__restrict__ bits, float2 *__restrict__ frames, long n_frames)
+{
+    __shared__ float2 s_tile[kWarpsPerBlock][kWarpTile];
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
+    TxWarp &tw_s = reinterpret_cast<TxWarp *>(s_raw)[warp];
+    float2 *tile = s_tile[warp] + grp * kGroupPitch;
+    Tw<EXACT> tw; tw.load(u);
+    int dmap[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmap[i] = c_tab.bin_data[8 * slot_m<EXACT>(i) + u];   // input index n <-> centred (n+32)%64
+    for (int i = lane; i < 4 * 160; i += 32) tw_s.img[i / 320][(i / 160) & 1][i % 160] = c_tab.lts_time[i % 160];      // LTS slot :573
+    __syncwarp();
+    const int k = grp & 1, sy = grp >> 1;                        // frame of the pair, symbol of the frame (half-warp partners: the two frames)
+    const long n_pairs = (n_frames + 1) / 2;
+    uint32_t it = 0;
+    for (long pr = (long)blockIdx.x * kWarpsPerBlock + warp; pr < n_pairs; pr += (long)gridDim.x * kWarpsPerBlock, ++it) {
+        const int st = (int)(it & 1u);
+        const long f = 2 * pr + k;
+        const bool active = f < n_frames;
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (active) { const uint32_t *w = bits + (f * 2 + sy) * 3; w0 = w[0]; w1 = w[1]; w2 = w[2]; }
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // grid value at centred index (n+32)%64 (ifft_shift :208), conjugated (:328)
+            const int d = dmap[i];
+            float2 x = make_float2(0.f, -0.f);
+            if (d >= 0) { x = qpsk_point(bit_pair(w0, w1, w2, d)); x.y = -x.y; }
+            else if (d == -2) x.x = 1.f;
+            else if (d == -3) x.x = -1.f;
+            v[i] = x;
+        }
+        fft64<EXACT>(v, tw, tile, u);
+        // the image set `st` was handed to the copy engine two passes ago: it must have been read before it is overwritten
+        if (lane == 0) tma::bulk_wait_read<1>();
+        __syncwarp();
+        float2 *dst = tw_s.img[st][k] + 160 + 80 * sy;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int np = u + 8 * ((j + 4) & 7);               // fft_shift inside ifft's fft() -> 32-sample rotation (Q4)
+            const float2 y = make_float2(v[j].x * 0.015625f, -v[j].y * 0.015625f);
+            dst[16 + np] = y;                                   // body :564
+            if (np >= 48) dst[np - 48] = y;                     // CP   :563
+        }
+        tma::fence_proxy_async();                               // generic-proxy writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+            tma::bulk_s2g(frames + (2 * pr) * 320, tma::saddr(tw_s.img[st][0]), 2560);
+            if (2 * pr + 1 < n_frames) tma::bulk_s2g(frames + (2 * pr + 1) * 320, tma::saddr(tw_s.img[st][1]), 2560);
+            tma::bulk_commit();
+        }
+    }
+    if (lane == 0) tma::bulk_wait_read<0>();                    // shared memory must outlive the copies that read it
+}
 
 constexpr int kStages = 2;          // the ring indexing below (k & 1, k >> 1) relies on it
 
@@ -754,8 +846,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
                     const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
                     const float2 G = cadd(A, B);
                     const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
-                    // items 0..31 belong to symbol 0, 64..95 to symbol 1, 32..63 split at lane 16
-                    const float rF = t == 0 ? rad.z : t == 2 ? rad.w : (lane < 16 ? rad.z : rad.w);
+                    const float rF = ic.f_off[t] < kWin ? rad.z : rad.w;               // the item's symbol
                     pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], w >> ic.shift[t], rF, rH2, den_min4, e2v, doubt);
                 }
                 f_e2 = e2v.x + e2v.y;
@@ -1177,19 +1268,28 @@ namespace ofdm {
 // tap l = normals (2l, 2l+1) of block l/2.  Same float operation order as the oracle (orc_apply_taps):
 // descending l, separate multiplies and adds (no FMA), so supplied taps reproduce it bit for bit.
 
+// The FIR-type kernels below (multipath taps, RRC shaping, matched filter) stage a frame through shared memory in tiles of
+// `tile` samples plus the filter's halo, one tile per warp and pass, so that the shared-memory footprint does not grow with the
+// frame length (any n_sym up to OFDM_MAX_SYM, any capture length); every output sample is still accumulated by one thread in
+// the reference's order, so tiling does not change a bit.
+constexpr int kFirTile = 2048;          // largest tile (samples per warp and pass)
+constexpr int kFirHalo = 32;            // room for the halo: 15 taps back (multipath), 20 samples back (RRC)
+inline int fir_tile(int samples) { int t = (samples + 31) & ~31; return t < kFirTile ? t : kFirTile; }
+inline size_t fir_smem_bytes(int tile) { return (size_t)kWarpsPerBlock * (tile + kFirHalo) * sizeof(float2); }
+
 template <bool PHILOX>
 __global__ void __launch_bounds__(kThreads) k_multipath(const float2 *__restrict__ tx, const float2 *__restrict__ taps, uint32_t seed,
                                                         uint64_t frame0, int n_taps, float2 *__restrict__ out, float2 *__restrict__ taps_out,
-                                                        long n_frames, int len)
+                                                        long n_frames, int len, int tile)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ float2 s_taps[kWarpsPerBlock][kMaxTaps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * (len + kMaxTaps);
-    float2 *sh = sx + len;
+    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * (tile + kFirHalo);
+    float2 *sh = s_taps[warp];
     const float scale = sqrtf(0.5f / (float)n_taps);
     for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
         const float2 *x = tx + f * len;
-        for (int i = lane; i < len; i += 32) sx[i] = x[i];
         if (PHILOX) {
             if (2 * lane < n_taps) {
                 float z[4];
@@ -1200,16 +1300,22 @@ __global__ void __launch_bounds__(kThreads) k_multipath(const float2 *__restrict
         } else if (lane < n_taps) sh[lane] = taps[f * n_taps + lane];
         __syncwarp();
         if (taps_out != nullptr && lane < n_taps) taps_out[f * n_taps + lane] = sh[lane];
-        for (int n = lane; n < len; n += 32) {
-            float ar = 0.f, ai = 0.f;
-            for (int l = (n_taps - 1 < n ? n_taps - 1 : n); l >= 0; --l) {
-                const float2 a = sx[n - l], b = sh[l];
-                ar = __fadd_rn(ar, __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)));
-                ai = __fadd_rn(ai, __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+        for (int n0 = 0; n0 < len; n0 += tile) {
+            const int n1 = n0 + tile < len ? n0 + tile : len;
+            const int lo = n0 - (kMaxTaps - 1) > 0 ? n0 - (kMaxTaps - 1) : 0;        // halo: the taps reach 15 samples back
+            for (int i = lo + lane; i < n1; i += 32) sx[i - lo] = x[i];
+            __syncwarp();
+            for (int n = n0 + lane; n < n1; n += 32) {
+                float ar = 0.f, ai = 0.f;
+                for (int l = (n_taps - 1 < n ? n_taps - 1 : n); l >= 0; --l) {
+                    const float2 a = sx[n - l - lo], b = sh[l];
+                    ar = __fadd_rn(ar, __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)));
+                    ai = __fadd_rn(ai, __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+                }
+                out[f * len + n] = make_float2(ar, ai);
             }
-            out[f * len + n] = make_float2(ar, ai);
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -1244,50 +1350,67 @@ __constant__ float c_rrc[21] = {-0.000454720514876223f, 0.00353689555574986f, -0
                                 0.00214368242727367f, 0.00757906190517828f, -0.00714560809091226f, 0.00353689555574986f,
                                 -0.000454720514876223f};
 
-__global__ void __launch_bounds__(kThreads) k_rrc_tx(const float2 *__restrict__ frames, float2 *__restrict__ out, long n_frames, int len)
+__global__ void __launch_bounds__(kThreads) k_rrc_tx(const float2 *__restrict__ frames, float2 *__restrict__ out, long n_frames, int len, int tile)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * len;
+    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * (tile + kFirHalo);
     const int n_out = 2 * len + 20;
     for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
-        for (int i = lane; i < len; i += 32) sx[i] = frames[f * len + i];
-        __syncwarp();
-        for (int k = lane; k < n_out; k += 32) {
-            const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < 2 * len - 1 ? k : 2 * len - 1;
-            float ar = 0.f, ai = 0.f;
-            for (int i = lo + (lo & 1); i <= hi; i += 2) {                  // even (non-stuffed) inputs, ascending
-                const float2 a = sx[i >> 1];
-                const float h = c_rrc[k - i];
-                ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
+        for (int k0 = 0; k0 < n_out; k0 += 2 * tile) {                        // 2 * tile outputs need tile + 10 inputs
+            const int k1 = k0 + 2 * tile < n_out ? k0 + 2 * tile : n_out;
+            const int j_lo = k0 >= 20 ? (k0 - 19) / 2 : 0;                    // first input sample (index i / 2) any of these outputs reads
+            const int j_hi = (k1 - 1) / 2 < len - 1 ? (k1 - 1) / 2 : len - 1;
+            for (int j = j_lo + lane; j <= j_hi; j += 32) sx[j - j_lo] = frames[f * len + j];
+            __syncwarp();
+            for (int k = k0 + lane; k < k1; k += 32) {
+                const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < 2 * len - 1 ? k : 2 * len - 1;
+                float ar = 0.f, ai = 0.f;
+                for (int i = lo + (lo & 1); i <= hi; i += 2) {                // even (non-stuffed) inputs, ascending
+                    const float2 a = sx[(i >> 1) - j_lo];
+                    const float h = c_rrc[k - i];
+                    ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
+                }
+                out[f * n_out + k] = make_float2(ar, ai);
             }
-            out[f * n_out + k] = make_float2(ar, ai);
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_rrc_rx(const float2 *__restrict__ in, float2 *__restrict__ out, long n_frames, int in_len,
-                                                     int packet_idx, int frame_len)
+// matched filter + decimation (:965, :986-996): output r reads the filtered sample k = p0 + 2 r, i.e. inputs k - 20 .. k.
+// idx == nullptr: the same packet index for every capture (ofdm_rrc_rx); else per capture (:978), and filtered samples
+// past the end of the capture (which the reference would read out of bounds when a packet starts late) count as zero.
+__global__ void __launch_bounds__(kThreads) k_rrc_rx(const float2 *__restrict__ in, const int32_t *__restrict__ idx, int packet_idx,
+                                                     float2 *__restrict__ out, long n_frames, int in_len, int frame_len, int tile)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * in_len;
+    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * (tile + kFirHalo);
+    const int r_tile = tile / 2;                                              // tile / 2 outputs need tile + 20 inputs
     for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
-        for (int i = lane; i < in_len; i += 32) sx[i] = in[f * in_len + i];
-        __syncwarp();
-        for (int r = lane; r < frame_len; r += 32) {
-            const int k = packet_idx + 2 * r;                               // :992-996
-            const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < in_len - 1 ? k : in_len - 1;
-            float ar = 0.f, ai = 0.f;
-            for (int i = lo; i <= hi; ++i) {
-                const float2 a = sx[i];
-                const float h = c_rrc[k - i];
-                ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
+        const int p0 = idx != nullptr ? idx[f] : packet_idx;
+        for (int r0 = 0; r0 < frame_len; r0 += r_tile) {
+            const int r1 = r0 + r_tile < frame_len ? r0 + r_tile : frame_len;
+            const int i_lo = p0 + 2 * r0 - 20 > 0 ? p0 + 2 * r0 - 20 : 0;
+            const int i_hi = p0 + 2 * (r1 - 1) < in_len - 1 ? p0 + 2 * (r1 - 1) : in_len - 1;
+            for (int i = i_lo + lane; i <= i_hi; i += 32) sx[i - i_lo] = in[f * in_len + i];
+            __syncwarp();
+            for (int r = r0 + lane; r < r1; r += 32) {
+                const int k = p0 + 2 * r;                                     // :992-996
+                float ar = 0.f, ai = 0.f;
+                if (k < in_len + 20) {
+                    const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < in_len - 1 ? k : in_len - 1;
+                    for (int i = lo; i <= hi; ++i) {
+                        const float2 a = sx[i - i_lo];
+                        const float h = c_rrc[k - i];
+                        ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
+                    }
+                }
+                out[f * frame_len + r] = make_float2(ar, ai);
             }
-            out[f * frame_len + r] = make_float2(ar, ai);
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -1299,38 +1422,42 @@ __global__ void __launch_bounds__(kThreads) k_rrc_rx(const float2 *__restrict__ 
 // no sliding-window reuse of the sums if the bits are to match.  What the lags do share is the summands: the float
 // product rx[n] * rx[n+16] (separately rounded multiplies, :674) and the double term cabs(rx[n])^2 (glibc hypot, :675) are
 // computed once per sample and staged in shared memory; each thread then runs its lag's two 32-term chains over them.
-__global__ void __launch_bounds__(kThreads) k_packet_detect(const float2 *__restrict__ rx, float *__restrict__ corr, long n, int len)
+// A capture is worked through in tiles of `tile` lags (+ 47 samples of halo), so that the footprint does not depend on its length.
+__global__ void __launch_bounds__(kThreads) k_packet_detect(const float2 *__restrict__ rx, float *__restrict__ corr, long n, int len, int tile)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     double *pk2 = reinterpret_cast<double *>(s_raw);
-    float2 *prod = reinterpret_cast<float2 *>(pk2 + len);
+    float2 *prod = reinterpret_cast<float2 *>(pk2 + tile + 48);
     const int n_corr = len - 47;
     for (long c = blockIdx.x; c < n; c += gridDim.x) {
         const float2 *x = rx + c * len;
-        for (int i = threadIdx.x; i < len; i += kThreads) {
-            const float2 a = x[i];
-            const double h = hypot_glibc((double)a.x, (double)a.y);          // cabs :675
-            pk2[i] = __dmul_rn(h, h);
-            if (i + 16 < len) {
-                const float2 b = x[i + 16];
-                prod[i] = make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),      // :674, float complex multiply
-                                      __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+        for (int i0 = 0; i0 < n_corr; i0 += tile) {
+            const int i1 = i0 + tile < n_corr ? i0 + tile : n_corr;
+            for (int sidx = i0 + threadIdx.x; sidx < i1 + 47; sidx += kThreads) {        // samples i0 .. i1 + 46 (< len)
+                const float2 a = x[sidx];
+                const double h = hypot_glibc((double)a.x, (double)a.y);          // cabs :675
+                pk2[sidx - i0] = __dmul_rn(h, h);
+                if (sidx + 16 < len) {
+                    const float2 b = x[sidx + 16];
+                    prod[sidx - i0] = make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),      // :674, float complex multiply
+                                                  __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+                }
             }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < n_corr; i += kThreads) {
-            float cr = 0.f, ci = 0.f, peak = 0.f;
+            __syncthreads();
+            for (int i = i0 + threadIdx.x; i < i1; i += kThreads) {
+                float cr = 0.f, ci = 0.f, peak = 0.f;
 #pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const float2 t = prod[i + k];
-                cr = __fadd_rn(cr, t.x);
-                ci = __fadd_rn(ci, t.y);
-                peak = __double2float_rn(__dadd_rn((double)peak, pk2[i + k + 16]));           // :675
+                for (int k = 0; k < 32; ++k) {
+                    const float2 t = prod[i - i0 + k];
+                    cr = __fadd_rn(cr, t.x);
+                    ci = __fadd_rn(ci, t.y);
+                    peak = __double2float_rn(__dadd_rn((double)peak, pk2[i - i0 + k + 16]));           // :675
+                }
+                const double hc = hypot_glibc((double)cr, (double)ci);
+                corr[c * n_corr + i] = __double2float_rn(__ddiv_rn(__dmul_rn(hc, hc), (double)__fmul_rn(peak, peak)));   // :677
             }
-            const double hc = hypot_glibc((double)cr, (double)ci);
-            corr[c * n_corr + i] = __double2float_rn(__ddiv_rn(__dmul_rn(hc, hc), (double)__fmul_rn(peak, peak)));   // :677
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -1450,33 +1577,4 @@ __global__ void k_prepend(const float2 *__restrict__ prefix, int prefix_len, con
         out[t] = j < prefix_len ? prefix[j] : in[f * len + (j - prefix_len)];
     }
 }
-// matched filter + decimation with a per-capture packet index (:965, :986-996).  Filtered samples past the end of
-// the capture (which the reference would read out of bounds when a packet starts late in the window) count as zero.
-__global__ void __launch_bounds__(kThreads) k_rrc_rx_idx(const float2 *__restrict__ in, const int32_t *__restrict__ idx, float2 *__restrict__ out,
-                                                         long n_frames, int in_len, int frame_len)
-{
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 *sx = reinterpret_cast<float2 *>(s_raw) + (size_t)warp * in_len;
-    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
-        for (int i = lane; i < in_len; i += 32) sx[i] = in[f * in_len + i];
-        __syncwarp();
-        const int p0 = idx[f];
-        for (int r = lane; r < frame_len; r += 32) {
-            const int k = p0 + 2 * r;
-            float ar = 0.f, ai = 0.f;
-            if (k < in_len + 20) {
-                const int lo = k - 20 < 0 ? 0 : k - 20, hi = k < in_len - 1 ? k : in_len - 1;
-                for (int i = lo; i <= hi; ++i) {
-                    const float2 a = sx[i];
-                    const float h = c_rrc[k - i];
-                    ar = __fadd_rn(ar, __fmul_rn(a.x, h)); ai = __fadd_rn(ai, __fmul_rn(a.y, h));
-                }
-            }
-            out[f * frame_len + r] = make_float2(ar, ai);
-        }
-        __syncwarp();
-    }
-}
-
 }  // namespace ofdm

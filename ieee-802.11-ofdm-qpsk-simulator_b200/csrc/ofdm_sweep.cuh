@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             GN[t] = cadd(ws.fn[0][bin], ws.fn[1][bin]);                        //               noise part
             FX[t] = (&ws.fx[2][0])[ic.f_off[t]];
             FN[t] = (&ws.fn[2][0])[ic.f_off[t]];
-            const bool sym0 = t == 0 || (t == 1 && lane < 16);                 // items 0..47 belong to symbol 0
+            const bool sym0 = ic.f_off[t] < kWin;                              // the item's symbol
             rFX[t] = sym0 ? rX.z : rX.w;
             rFN[t] = sym0 ? rN.z : rN.w;
         }
