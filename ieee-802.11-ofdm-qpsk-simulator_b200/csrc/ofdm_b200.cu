@@ -219,10 +219,10 @@ void set_radius(ofdm_ctx *ctx, RxParams &q)
 template <int NOISE>
 int launch_stream_n_mode(ofdm_ctx *ctx, int mode, const RxParams &p)
 {
-    if (mode != OFDM_MODE_EXACT) return launch_stream_n<kArithFast, NOISE>(ctx, p);
-    if (!ctx->checked) return launch_stream_n<kArithExact, NOISE>(ctx, p);
+    if (mode == OFDM_MODE_EXACT && !ctx->checked) return launch_stream_n<kArithExact, NOISE>(ctx, p);
     RxParams q = p;
-    set_radius(ctx, q);
+    set_radius(ctx, q);                 // fast mode keeps the EVM guard (tiny |H| bins are replayed exactly), exact mode verifies every decision
+    if (mode != OFDM_MODE_EXACT) return launch_stream_n<kArithFast, NOISE>(ctx, q);
     return launch_stream_n<kArithChecked, NOISE>(ctx, q);
 }
 
@@ -252,9 +252,11 @@ int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
             if (noise == kNoiseInject) return launch_stream<kArithExact, kNoiseInject>(ctx, p);
             return launch_stream<kArithExact, kNoisePhilox>(ctx, p);
         }
-        if (noise == kNoiseNone) return launch_stream<kArithFast, kNoiseNone>(ctx, p);
-        if (noise == kNoiseInject) return launch_stream<kArithFast, kNoiseInject>(ctx, p);
-        return launch_stream<kArithFast, kNoisePhilox>(ctx, p);
+        RxParams q = p;
+        set_radius(ctx, q);             // the EVM guard of the fast kernels
+        if (noise == kNoiseNone) return launch_stream<kArithFast, kNoiseNone>(ctx, q);
+        if (noise == kNoiseInject) return launch_stream<kArithFast, kNoiseInject>(ctx, q);
+        return launch_stream<kArithFast, kNoisePhilox>(ctx, q);
     }
     if (mode == OFDM_MODE_EXACT) {
         if (noise == kNoiseNone) return launch_rx_d<true, kNoiseNone>(ctx, dump, p);

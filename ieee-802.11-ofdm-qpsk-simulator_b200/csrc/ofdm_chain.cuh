@@ -181,6 +181,7 @@ struct WarpShared {
     float2 tile[kWarpTile];         // transform transpose tile, then the F exchange tile (2 x kWin used)
     float2 lts[2][kWin];            // FFT of the two received LTS halves
     float2 body[2][kWin];           // the frame's two symbol bodies in time (skewed windows)
+    uint2 res[kMaxSnr];             // per SNR point of the current frame: {packed rail errors, sum |e|^2}, booked once per frame
 };
 
 // Replay of one (frame, SNR point) of the Monte-Carlo kernel in the reference's arithmetic (rare path of kArithChecked):
@@ -388,7 +389,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
             if (lane < p.n_snr) sig_lo = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane]));
             if (lane + 32 < p.n_snr) sig_hi = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane + 32]));
         }
+        // The warp sums of a point (one REDUX, five dependent shuffles) are finished one iteration late, on top of the next
+        // point's Philox rounds, and the owner lanes book all points of the frame at once from ws.res (no per-point branch).
+        uint32_t pk_pend = 0;
+        float e2_pend = 0.f;
         for (int si = 0; si < p.n_snr; ++si) {
+            {
+                float rs = e2_pend;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                if (lane == 0 && si > 0) ws.res[si - 1] = make_uint2(pk_pend, __float_as_uint(rs));
+            }
             double sigma_d = 0.0; float sigma_f;
             if (TX_EXACT) {
                 sigma_d = __shfl_sync(0xffffffffu, si < 32 ? sig_lo : sig_hi, si & 31);
@@ -450,21 +461,29 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 }
                 __syncwarp();
             }
-            pk = __reduce_add_sync(0xffffffffu, pk);                // one REDUX: the three 8-bit fields stay below 97
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-            float evm;
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(evm) : "f"(e2 * inv_ref2));                 // :1124
-            if (lane == (si & 31)) {                                   // the lane that owns this SNR point books the frame
-                if (si < 32) {
-                    m_i[0] += pk & 0xFFu; m_q[0] += (pk >> 8) & 0xFFu; m_b[0] += pk >> 16; m_ferr[0] += pk != 0u;
-                    m_e2[0] += e2; m_evm[0] += evm;
-                } else {
-                    m_i[1] += pk & 0xFFu; m_q[1] += (pk >> 8) & 0xFFu; m_b[1] += pk >> 16; m_ferr[1] += pk != 0u;
-                    m_e2[1] += e2; m_evm[1] += evm;
-                }
-            }
+            pk_pend = __reduce_add_sync(0xffffffffu, pk);           // one REDUX: the three 8-bit fields stay below 97
+            e2_pend = e2;
         }
+        {
+            float rs = e2_pend;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            if (lane == 0) ws.res[p.n_snr - 1] = make_uint2(pk_pend, __float_as_uint(rs));
+        }
+        __syncwarp();
+        // the lane that owns an SNR point books the frame's result for it (lanes beyond n_snr read stale words and add nothing)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint2 rr = ws.res[lane + 32 * h];
+            const bool mine = lane + 32 * h < p.n_snr;
+            const uint32_t pkh = mine ? rr.x : 0u;
+            const float e2h = mine ? __uint_as_float(rr.y) : 0.f;
+            float evm;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(evm) : "f"(e2h * inv_ref2));                // :1124
+            m_i[h] += pkh & 0xFFu; m_q[h] += (pkh >> 8) & 0xFFu; m_b[h] += pkh >> 16; m_ferr[h] += pkh != 0u;
+            m_e2[h] += e2h; m_evm[h] += evm;
+        }
+        __syncwarp();
         n_done += 1;
         if ((n_done & 63u) == 0u) {
 #pragma unroll
@@ -718,13 +737,18 @@ __device__ __noinline__ uint2 stream_frame_replay(const float2 *frame, const flo
 
 // resident blocks per SM the launch bounds ask for: the fp32 kernels fit three (80 registers, <= 75 KB shared)
 static_assert(sizeof(StreamStage<false>) % 16 == 0 && sizeof(StreamStage<true>) % 16 == 0 && sizeof(StreamWarp<false>) % 16 == 0, "stage alignment");
-template <int ARITH, int NOISE> constexpr int stream_blocks_per_sm() { return (ARITH == kArithFast && NOISE != kNoiseInject) ? 3 : 2; }
+#ifndef OFDM_FAST_STREAM_BLOCKS
+#define OFDM_FAST_STREAM_BLOCKS 3       // A/B knob (tools/ab.sh): resident blocks per SM of the fast kernels without injected draws
+#endif
+template <int ARITH, int NOISE> constexpr int stream_blocks_per_sm() { return (ARITH == kArithFast && NOISE != kNoiseInject) ? OFDM_FAST_STREAM_BLOCKS : 2; }
 
 template <int ARITH, int NOISE>
 __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()) k_stream_rx2(RxParams p)
 {
     constexpr bool EXACT = ARITH == kArithExact;                // transform / decision arithmetic of the main path
     constexpr bool CHECKED = ARITH == kArithChecked;
+    constexpr bool SPEC = ARITH != kArithExact;                 // fp32 speculation + exact replay: every rail decision verified (checked) or the EVM guard only (fast)
+    constexpr int LEVEL = CHECKED ? 2 : 1;
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
     __shared__ double s_sum[kWarpsPerBlock][2];
@@ -819,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
                 float2 smp = ws.st[s].x[grp][u + 8 * m];
                 if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);   // CHECKED: speculated (kChanRadius)
                 if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
-                if (CHECKED) n2 = __ffma2_rn(smp, smp, n2);
+                if (SPEC) n2 = __ffma2_rn(smp, smp, n2);
                 v[i] = smp;
             }
             __syncwarp();                                         // every lane has its samples: the stage can be refilled
@@ -828,14 +852,14 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
             float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[u + 8 * j] = v[j];
-            if (CHECKED) {
+            if (SPEC) {
                 const float r = window_radius(n2, p.radius_scale, NOISE != kNoiseNone ? p.radius_chan * sigma_f : 0.f);
                 if (u == 0) ws.radius[grp] = r;
             }
             __syncwarp();
             float f_e2 = 0.f;
             uint32_t pk = 0;
-            if (CHECKED) {
+            if (SPEC) {
                 float2 e2v = make_float2(0.f, 0.f);
                 const float4 rad = *reinterpret_cast<const float4 *>(ws.radius);
                 const float rH2 = rad.x + rad.y;                                  // 2 r_H
@@ -847,7 +871,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
                     const float2 G = cadd(A, B);
                     const uint32_t w = t == 0 ? w0 : t == 1 ? w1 : w2;
                     const float rF = ic.f_off[t] < kWin ? rad.z : rad.w;               // the item's symbol
-                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], w >> ic.shift[t], rF, rH2, den_min4, e2v, doubt);
+                    pk += process_bin_spec<LEVEL>(ws.tile[ic.f_off[t]], G, k4[t], w >> ic.shift[t], rF, rH2, den_min4, e2v, doubt);
                 }
                 f_e2 = e2v.x + e2v.y;
                 __syncwarp();
@@ -1000,6 +1024,8 @@ template <int ARITH, int NOISE>
 __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
 {
     constexpr bool EXACT = ARITH == kArithExact, CHECKED = ARITH == kArithChecked;
+    constexpr bool SPEC = ARITH != kArithExact;                 // see k_stream_rx2
+    constexpr int LEVEL = CHECKED ? 2 : 1;
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[kWarpsPerBlock][4];
     __shared__ double s_sum[kWarpsPerBlock][2];
@@ -1124,23 +1150,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                         if (NOISE == kNoiseInject) smp.x = add_noise<EXACT>(smp.x, ws.st[s].g[grp][u + 8 * m], sigma_d, sigma_f);   // CHECKED: speculated
                         if (NOISE == kNoisePhilox) smp.x = add_noise<EXACT>(smp.x, z[m], sigma_d, sigma_f);
                     }
-                    if (CHECKED) n2 = __ffma2_rn(smp, smp, n2);
+                    if (SPEC) n2 = __ffma2_rn(smp, smp, n2);
                     v[i] = smp;
                 }
                 __syncwarp();                                     // every lane has its samples: the stage can be refilled
                 issue_next(s);
                 fft64<EXACT>(v, tw, tile, u);
                 float rad = 0.f;
-                if (CHECKED) rad = window_radius(n2, p.radius_scale, NOISE != kNoiseNone ? p.radius_chan * sigma_f : 0.f);
+                if (SPEC) rad = window_radius(n2, p.radius_scale, NOISE != kNoiseNone ? p.radius_chan * sigma_f : 0.f);
                 uint32_t pk = 0;
                 if (pass == 0) {
                     float2 *dst = grp < 2 ? ws.lts[grp] : ws.tile + (grp - 2) * kWin;
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) dst[u + 8 * jj] = v[jj];
-                    if (CHECKED && u == 0) ws.radius[grp] = rad;
+                    if (SPEC && u == 0) ws.radius[grp] = rad;
                     __syncwarp();
                     float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (CHECKED) {
+                    if (SPEC) {
                         r4 = *reinterpret_cast<const float4 *>(ws.radius);
                         rH2 = r4.x + r4.y;                                        // 2 r_H, kept for the frame's later passes
                     }
@@ -1153,10 +1179,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                         const uint32_t w = wq[t];
                         float e2 = 0.f;
                         uint32_t r;
-                        if (CHECKED) {
+                        if (SPEC) {
                             bool dbt = false;
                             float2 e2v = make_float2(0.f, 0.f);
-                            r = process_bin_checked(ws.tile[ic.f_off[t]], cadd(A, B), 4.f * ic.sc[t], w >> ic.shift[t],
+                            r = process_bin_spec<LEVEL>(ws.tile[ic.f_off[t]], cadd(A, B), 4.f * ic.sc[t], w >> ic.shift[t],
                                                     isym == 0 ? r4.z : r4.w, rH2, den_min4, e2v, dbt);
                             e2 = e2v.x + e2v.y;
                             doubt = doubt || (valid && dbt);
@@ -1172,10 +1198,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                     float2 *dst = ws.tile + grp * kWin;
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) dst[u + 8 * jj] = v[jj];
-                    if (CHECKED && u == 0) ws.radius[grp] = rad;
+                    if (SPEC && u == 0) ws.radius[grp] = rad;
                     __syncwarp();
                     float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (CHECKED) r4 = *reinterpret_cast<const float4 *>(ws.radius);
+                    if (SPEC) r4 = *reinterpret_cast<const float4 *>(ws.radius);
                     const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
 #pragma unroll
                     for (int round = 0; round < 2; ++round) {
@@ -1188,11 +1214,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                             const float2 F = ws.tile[2 * round * kWin + ic.f_off[t]];
                             float e2 = 0.f;
                             uint32_t r;
-                            if (CHECKED) {
+                            if (SPEC) {
                                 bool dbt = false;
                                 float2 e2v = make_float2(0.f, 0.f);
                                 const float rF = round == 0 ? (isym == 0 ? r4.x : r4.y) : (isym == 0 ? r4.z : r4.w);
-                                r = process_bin_checked(F, cadd(A, B), 4.f * ic.sc[t], w >> ic.shift[t], rF, rH2, den_min4, e2v, dbt);
+                                r = process_bin_spec<LEVEL>(F, cadd(A, B), 4.f * ic.sc[t], w >> ic.shift[t], rF, rH2, den_min4, e2v, dbt);
                                 e2 = e2v.x + e2v.y;
                                 doubt = doubt || (valid && dbt);
                             } else {
@@ -1206,7 +1232,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                 f_i += pk & 0xFFu; f_q += (pk >> 8) & 0xFFu; f_both += pk >> 16;
                 __syncwarp();
             }
-            if (CHECKED) {
+            if (SPEC) {
                 if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay the frame exactly
                     SweepFrame fr;
                     fr.x = p.in + f * len; fr.g = NOISE == kNoiseInject ? p.g + f * len : nullptr; fr.bits = fbits; fr.n_sym = n_sym;

@@ -107,15 +107,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
     for (long f = f_first; f < p.n_frames; f += stride, ++k) {
         const int s = (int)(k & 1u);
         const uint32_t phase = (k >> 1) & 1u;
+        // global loads first; what depends on them (noise scales, bit pairs) is computed after the transforms, which hide their latency
         const float P = p.power[f];
         const uint32_t *wb = p.tx_bits + f * 6;
-        uint32_t txp[3];
+        uint32_t txw[3];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) txp[t] = wb[ic.word[t]] >> ic.shift[t];
-        // the noise scale of every SNR point, (float)sqrt((double)(P / snr)) (:647, :651), one (two) per lane
-        float sig_lo = 0.f, sig_hi = 0.f;
-        if (lane < p.n_snr) sig_lo = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane])));
-        if (lane + 32 < p.n_snr) sig_hi = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane + 32])));
+        for (int t = 0; t < 3; ++t) txw[t] = wb[ic.word[t]];
 
         tma::wait_addr(bar0 + 8u * (uint32_t)s, phase);
         float2 v[8];
@@ -170,12 +167,29 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             rFN[t] = sym0 ? rN.z : rN.w;
         }
         __syncwarp();                                         // everyone holds its items: fx / fn may be overwritten
+        uint32_t txp[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) txp[t] = txw[t] >> ic.shift[t];
+        // the noise scale of every SNR point, (float)sqrt((double)(P / snr)) (:647, :651), one (two) per lane
+        float sig_lo = 0.f, sig_hi = 0.f;
+        if (lane < p.n_snr) sig_lo = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane])));
+        if (lane + 32 < p.n_snr) sig_hi = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane + 32])));
 
         // ---- SNR loop OFDM.c:1202: one packed multiply-add per value, then the decision stage.  Per-point results
         // {packed rail errors, sum |e|^2} go through 64 words of shared memory (the noise tiles are free by now and the
         // replay does not touch them) so that the owner lanes book them once per frame instead of branching per point.
+        // The warp sums of a point (one REDUX for the packed counts, five dependent shuffles for sum |e|^2) are finished one
+        // iteration late, at the top of the next point's straight-line arithmetic, so that their latency is covered by it.
         uint2 *res = reinterpret_cast<uint2 *>(&ws.fn[0][0]);
+        uint32_t pk_pend = 0;
+        float e2_pend = 0.f;
         for (int si = 0; si < p.n_snr; ++si) {
+            {
+                float r = e2_pend;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                if (lane == 0 && si > 0) res[si - 1] = make_uint2(pk_pend, __float_as_uint(r));
+            }
             const float sg = __shfl_sync(0xffffffffu, si < 32 ? sig_lo : sig_hi, si & 31);
             const float2 sg2 = make_float2(sg, sg);
             const float rH2 = fmaf(sg, rHN, rHX);
@@ -197,10 +211,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
                                                                   ws.tile, &ws.fx[0][0]);
                 pk = r.x; e2 = __uint_as_float(r.y);
             }
-            pk = __reduce_add_sync(0xffffffffu, pk);                // one REDUX: the three 8-bit fields stay below 97
+            pk_pend = __reduce_add_sync(0xffffffffu, pk);           // one REDUX: the three 8-bit fields stay below 97
+            e2_pend = e2;
+        }
+        {
+            float r = e2_pend;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-            if (lane == 0) res[si] = make_uint2(pk, __float_as_uint(e2));      // booked once per frame, below
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (lane == 0) res[p.n_snr - 1] = make_uint2(pk_pend, __float_as_uint(r));           // booked once per frame, below
         }
         __syncwarp();
         // the lane that owns an SNR point books the frame's result for it (lanes beyond n_snr read stale words and add nothing)

@@ -2,6 +2,8 @@
 EXACT mode: bit-exact IQ / decisions / counts.  FAST mode: 1e-5 relative (to the array's peak
 magnitude) on IQ, 1e-5 relative on EVM; decisions may differ only where a rail sits within
 rounding distance of zero."""
+import os
+
 import numpy as np
 import pytest
 
@@ -131,16 +133,29 @@ def test_receiver_fast(ofdm, pkg, port, n_sym, snr):
     cnt, d = ofdm.awgn_rx_inject(frames, gd, packed, snr, n_sym, pkg.MODE_FAST, power=power,
                                  want=("H", "eq", "frame_bit_errors", "frame_evm_lin"))
     assert close_rel(d["H"].cpu().numpy(), want["H"])
-    # equalised points: relative to each frame's peak magnitude (a near-zero H bin blows one frame up)
+    # Per-bin dumps come from the generic kernel, plain fp32 end to end.  Equalised points relative to each frame's peak
+    # magnitude: a bin whose channel estimate is nearly zero amplifies the fp32 transform's error in H, so single frames
+    # deviate by more than 1e-5 (the measured worst figures go to $OFDM_TEST_LOG when set; DESIGN.md section 4 quotes them).
     eq, weq = d["eq"].cpu().numpy().astype(np.float64), want["eq"].astype(np.float64)
     scale = np.abs(weq).reshape(n_frames, -1).max(axis=1)[:, None, None]
-    assert np.max(np.abs(eq - weq) / scale) <= 20 * REL
-    assert np.allclose(d["frame_evm_lin"].cpu().numpy(), want["evm_lin"], rtol=20 * REL)
+    worst_eq = np.max(np.abs(eq - weq) / scale)
+    worst_evm = np.max(np.abs(d["frame_evm_lin"].cpu().numpy() / want["evm_lin"] - 1))
+    if os.environ.get("OFDM_TEST_LOG"):
+        with open(os.environ["OFDM_TEST_LOG"], "a") as f:
+            f.write("test_receiver_fast n_sym=%d snr=%.1f worst |eq - ref| / frame peak %.3e, worst per-frame EVM rel %.3e\n" % (n_sym, snr, worst_eq, worst_evm))
+    assert worst_eq <= 20 * REL and worst_evm <= 20 * REL, (worst_eq, worst_evm)
     diff = np.abs(d["frame_bit_errors"].cpu().numpy() - want["bit_errors"])
     assert diff.sum() <= 2          # decisions differ only for rails within fp32 rounding of zero
-    evm_gpu = np.sqrt(cnt.sum_err2 / cnt.sum_ref2)
+    # The EVM the path reports (batch totals, streaming kernels) meets the 1e-5 of the north star in FAST mode too: those
+    # kernels replay the few frames with a tiny |H| bin in the reference's arithmetic (the EVM guard of ofdm_chain.cuh).
     evm_cpu = np.sqrt(np.sum(want["evm_lin"].astype(np.float64) ** 2) / n_frames)
-    assert abs(evm_gpu - evm_cpu) <= 20 * REL * evm_cpu
+    tot, _ = ofdm.awgn_rx_inject(frames, gd, packed, snr, n_sym, pkg.MODE_FAST, power=power)
+    evm_gpu = np.sqrt(tot.sum_err2 / tot.sum_ref2)
+    assert abs(evm_gpu - evm_cpu) <= REL * evm_cpu, (evm_gpu, evm_cpu)
+    assert abs(tot.sum_evm_lin - float(np.sum(want["evm_lin"].astype(np.float64)))) <= REL * float(np.sum(want["evm_lin"].astype(np.float64)))
+    assert abs(int(tot.bit_errors) - int(want["bit_errors"].sum())) <= 2
+    sw = ofdm.sweep_inject_dev(packed, gd, n_frames, n_sym, [snr], pkg.MODE_FAST)[0]           # the all-SNR kernel (n_sym = 2) / per-point route
+    assert abs(np.sqrt(sw.sum_err2 / sw.sum_ref2) - evm_cpu) <= REL * evm_cpu
 
 
 @pytest.mark.parametrize("mode", [0, 1])
