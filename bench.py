@@ -615,7 +615,8 @@ def run_gpu(args):
                              "bytes_per_launch": BYTES_PER_FRAME_PASS * n_frames, "kernel_ms": k_ms,
                              "timed": "%d launches (one per SNR point, %d sweeps) through ofdm_awgn_rx_inject in this run, CUDA events per launch"
                                       % (len(kernel_ms), args.steps),
-                             "sweep_ms_if_launched_per_point": k_ms * n_snr},
+                             "sweep_ms_if_launched_per_point": k_ms * n_snr,
+                             "kernel_ms_by_snr_point": [round(float(np.mean(kernel_ms[i::n_snr])), 4) for i in range(n_snr)]},
                 "sweep_kernel": dict({"kernel": "k_sweep_lin<checked>", "kernel_ms": sweep_kernel_ms, "share_of_step": sweep_kernel_ms / ms_step,
                                       "bound": "instruction issue (the frame and its draws cross HBM once per sweep)",
                                       "hbm_GBps": BYTES_PER_FRAME_PASS * n_frames / (sweep_kernel_ms * 1e-3) / 1e9,

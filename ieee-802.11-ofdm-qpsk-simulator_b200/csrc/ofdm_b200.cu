@@ -31,6 +31,7 @@ struct ofdm_ctx {
     float lts_time[320];
     float sts_time[320];
     float *sts_dev = nullptr;
+    unsigned long long *replayed_dev = nullptr;  // frames / points the speculating kernels replayed exactly (this context)
     float lts_power_prefix = 0.0f;
     // cached scratch (grown on demand, released with the context)
     void *scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -212,6 +213,7 @@ int launch_stream_n(ofdm_ctx *ctx, const RxParams &p)
 // error radii of the speculating EXACT kernels (ofdm_chain.cuh: kRadius, kChanRadius)
 void set_radius(ofdm_ctx *ctx, RxParams &q)
 {
+    q.replayed = ctx->replayed_dev;
     q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
     q.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf((float)OFDM_FRAME_LEN(q.n_sym) * q.snr_lin) * 1.001f;
 }
@@ -392,6 +394,10 @@ int ofdm_ctx_create(ofdm_ctx **out, int device)
         dt.ready = true;
     }
     }
+    if (st == OFDM_OK) {
+        if (cudaMalloc(&ctx->replayed_dev, sizeof(unsigned long long)) != cudaSuccess) st = OFDM_ERR_NOMEM;
+        else if (cudaMemset(ctx->replayed_dev, 0, sizeof(unsigned long long)) != cudaSuccess) st = OFDM_ERR_CUDA;
+    }
     if (st == OFDM_OK) {            // per-context device copy of the STS slot (ofdm_prepend_sts)
         if (cudaMalloc(&ctx->sts_dev, sizeof ctx->sts_time) != cudaSuccess) st = OFDM_ERR_NOMEM;
         else if (cudaMemcpy(ctx->sts_dev, ctx->sts_time, sizeof ctx->sts_time, cudaMemcpyHostToDevice) != cudaSuccess) st = OFDM_ERR_CUDA;
@@ -409,6 +415,7 @@ int ofdm_ctx_destroy(ofdm_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 6; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->sts_dev) cudaFree(ctx->sts_dev);
+    if (ctx->replayed_dev) cudaFree(ctx->replayed_dev);
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
@@ -454,9 +461,9 @@ int ofdm_ctx_replayed_frames(ofdm_ctx *ctx, uint64_t *count, int reset)
     OFDM_REQUIRE(ctx, count != nullptr);
     unsigned long long v = 0;
     OFDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    OFDM_CUDA(ctx, cudaMemcpyFromSymbol(&v, g_replayed_frames, sizeof v));
+    OFDM_CUDA(ctx, cudaMemcpy(&v, ctx->replayed_dev, sizeof v, cudaMemcpyDeviceToHost));
     *count = v;
-    if (reset) { v = 0; OFDM_CUDA(ctx, cudaMemcpyToSymbol(g_replayed_frames, &v, sizeof v)); }
+    if (reset) OFDM_CUDA(ctx, cudaMemset(ctx->replayed_dev, 0, sizeof v));
     return OFDM_OK;
 }
 int ofdm_ctx_sm_count(const ofdm_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
@@ -905,6 +912,7 @@ int sweep_points(ofdm_ctx *ctx, const float *frames, const float *g, const float
         p.n_snr = n_snr - s0 < kMaxSnr ? n_snr - s0 : kMaxSnr;
         for (int i = 0; i < p.n_snr; ++i) p.snr_lin[i] = snr_linear(snr_db[s0 + i]);
         p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+        p.replayed = ctx->replayed_dev;
         p.counters = counters + s0;
         for (long f0 = 0; f0 < n_frames; f0 += max_frames) {
             p.n_frames = n_frames - f0 < max_frames ? n_frames - f0 : max_frames;
@@ -959,6 +967,7 @@ int mc_awgn_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, i
                 p.stream[i] = streams ? streams[i] : (uint32_t)i;
             }
             p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+            p.replayed = ctx->replayed_dev;
             p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
             auto launch = [&](auto k) -> int {
                 OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1143,6 +1152,7 @@ int mc_multipath_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_fram
                 p.stream[i] = streams ? streams[i] : (uint32_t)i;
             }
             p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
+            p.replayed = ctx->replayed_dev;
             p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
             auto launch = [&](auto k) -> int {
                 OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

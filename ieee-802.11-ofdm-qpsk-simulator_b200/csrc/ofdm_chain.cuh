@@ -97,7 +97,8 @@ enum { kArithFast = 0, kArithExact = 1, kArithChecked = 2 };
 constexpr float kRadius = 512.f * 5.9604645e-8f;
 constexpr float kChanRadius = 18.f * 5.9604645e-8f;
 
-__device__ unsigned long long g_replayed_frames;     // frames the checked kernels replayed exactly (statistics)
+// frames the speculating kernels replayed exactly are counted per context (a device word owned by the ofdm_ctx, passed in the
+// kernel parameters as `replayed`)
 
 // radius of one window from the lane's share of sum |x|^2; windows whose energy is outside [1e-30, 1e20] are never
 // trusted (squares may have underflowed / the magnitude guards of the decision would not hold)
@@ -174,6 +175,7 @@ struct McParams {
     float radius_chan;              // kArithChecked: kChanRadius * sqrt(320) (times sqrt(P) = the channel term), or infinity
     int n_taps;                     // multipath variant: taps per frame (1..kMaxTaps)
     ofdm_counters *counters;        // [n_snr], accumulated into
+    unsigned long long *replayed;   // the context's count of exactly replayed (frame, SNR point)s
 };
 
 // per-warp shared memory of the fused kernels
@@ -188,7 +190,7 @@ struct WarpShared {
 // the same Philox draws, exact channel, exact transform, exact decision stage.  txp3: the lane's three bit pairs,
 // two bits each.  Returns {packed rail errors, lane's sum |e|^2}, not yet reduced over the warp.
 __device__ __noinline__ uint2 mc_point_replay(const float2 *src, double sigma_d, uint32_t seed, uint32_t stream, uint64_t fr,
-                                              uint32_t txp3, float2 *ws_tile, float2 *ws_lts)
+                                              uint32_t txp3, float2 *ws_tile, float2 *ws_lts, unsigned long long *replayed)
 {
     const int lane = threadIdx.x & 31, grp = lane >> 3, u = lane & 7;
     Tw<true> tw; tw.load(u);
@@ -219,7 +221,7 @@ __device__ __noinline__ uint2 mc_point_replay(const float2 *src, double sigma_d,
         pk += item_eval<true>(ws_tile[ic.f_off[t]], Hh, ic.sc[t], (txp3 >> (2 * t)) & 3u, e2);
     }
     __syncwarp();
-    if (lane == 0) atomicAdd(&g_replayed_frames, 1ull);
+    if (lane == 0 && replayed != nullptr) atomicAdd(replayed, 1ull);
     return make_uint2(pk, __float_as_uint(e2));
 }
 
@@ -241,6 +243,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
     constexpr bool EXACT = ARITH == kArithExact;                // receiver arithmetic of the main path
     constexpr bool CHECKED = ARITH == kArithChecked;
     constexpr bool TX_EXACT = EXACT || CHECKED;                 // transmitter, power, channel
+    constexpr bool SPEC = ARITH != kArithExact;                 // fp32 receiver + exact replay: all decisions verified (checked) or the EVM guard only (fast)
+    constexpr int LEVEL = CHECKED ? 2 : 1;
     extern __shared__ __align__(128) unsigned char s_raw[];
     WarpShared *ws_all = reinterpret_cast<WarpShared *>(s_raw);
     float2 *s_ltsx = reinterpret_cast<float2 *>(s_raw + sizeof(WarpShared) * kWarpsPerBlock);   // [2][kWin] LTS halves, time
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 sigma_d = __shfl_sync(0xffffffffu, si < 32 ? sig_lo : sig_hi, si & 31);
                 sigma_f = (float)sigma_d;
                 if (EXACT) sigma_d = __dmul_rn(sigma_d, kTwScale);          // add_noise_s (the all-exact kernel is XU-bound)
-            } else sigma_f = sqrtP * p.inv_sqrt_snr[si];
+            } else { sigma_f = sqrtP * p.inv_sqrt_snr[si]; sigma_d = (double)sigma_f; }      // (the replay of a guarded bin uses the same scale)
             float za[4], zb[4];
             const uint32_t stream = p.stream[si];
             philox_normals4(p.seed, stream, fr, (uint32_t)blk_base, kDomainNoise, za);
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 const int m = slot_m<EXACT>(i);
                 float2 s = src[u + 8 * m];
                 const float z = m < 4 ? za[m & 3] : zb[m & 3];
-                if (CHECKED) { s.x = fmaf(sigma_f, z, s.x); n2 = __ffma2_rn(s, s, n2); }      // speculated channel (see kChanRadius)
+                if (SPEC) { s.x = fmaf(sigma_f, z, s.x); n2 = __ffma2_rn(s, s, n2); }         // speculated channel (see kChanRadius)
                 else s.x = add_noise_s<EXACT>(s.x, z, sigma_d, sigma_f);
                 r[i] = s;
             }
@@ -427,11 +431,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[u + 8 * j] = r[j];
             float rad = 0.f;
-            if (CHECKED) rad = window_radius(n2, p.radius_scale, p.radius_chan * sqrtP);
+            if (SPEC) rad = window_radius(n2, p.radius_scale, p.radius_chan * sqrtP);
             __syncwarp();
             float e2 = 0.f;
             uint32_t pk = 0;
-            if (CHECKED) {
+            if (SPEC) {
                 float2 e2v = make_float2(0.f, 0.f);
                 const float rA = __shfl_sync(0xffffffffu, rad, 0), rB = __shfl_sync(0xffffffffu, rad, 8);
                 const float r0 = __shfl_sync(0xffffffffu, rad, 16), r1 = __shfl_sync(0xffffffffu, rad, 24);
@@ -443,13 +447,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                     const float2 A = ws.lts[0][ic.bin[t]], B = ws.lts[1][ic.bin[t]];
                     const float2 G = cadd(A, B);
                     const float rF = ic.f_off[t] < kWin ? r0 : r1;
-                    pk += process_bin_checked(ws.tile[ic.f_off[t]], G, k4[t], txp[t], rF, rH2, den_min4, e2v, doubt);
+                    pk += process_bin_spec<LEVEL>(ws.tile[ic.f_off[t]], G, k4[t], txp[t], rF, rH2, den_min4, e2v, doubt);
                 }
                 e2 = e2v.x + e2v.y;
                 __syncwarp();
-                if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
+                if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions / EVM: replay exactly
                     const uint32_t txp3 = (txp[0] & 3u) | ((txp[1] & 3u) << 2) | ((txp[2] & 3u) << 4);
-                    const uint2 rr = mc_point_replay(src, sigma_d, p.seed, stream, fr, txp3, ws.tile, &ws.lts[0][0]);
+                    const uint2 rr = mc_point_replay(src, sigma_d, p.seed, stream, fr, txp3, ws.tile, &ws.lts[0][0], p.replayed);
                     pk = rr.x; e2 = __uint_as_float(rr.y);
                 }
             } else {
@@ -693,7 +697,8 @@ template <bool WITH_DRAWS> struct alignas(16) StreamWarp {
 // memory, exact channel, exact transform, exact decision stage.  Returns {packed rail errors, lane's sum |e|^2}.
 template <int NOISE>
 __device__ __noinline__ uint2 stream_frame_replay(const float2 *frame, const float *draws, const uint32_t *wb, double sigma_d,
-                                                  uint32_t seed, uint32_t stream, uint64_t frame_id, float2 *ws_tile, float2 *ws_lts)
+                                                  uint32_t seed, uint32_t stream, uint64_t frame_id, float2 *ws_tile, float2 *ws_lts,
+                                                  unsigned long long *replayed)
 {
     const int lane = threadIdx.x & 31, grp = lane >> 3, u = lane & 7;
     Tw<true> tw; tw.load(u);
@@ -731,14 +736,15 @@ __device__ __noinline__ uint2 stream_frame_replay(const float2 *frame, const flo
         pk += item_eval<true>(ws_tile[ic.f_off[t]], Hh, ic.sc[t], wb[ic.word[t]] >> ic.shift[t], e2);
     }
     __syncwarp();
-    if (lane == 0) atomicAdd(&g_replayed_frames, 1ull);
+    if (lane == 0 && replayed != nullptr) atomicAdd(replayed, 1ull);
     return make_uint2(pk, __float_as_uint(e2));
 }
 
-// resident blocks per SM the launch bounds ask for: the fp32 kernels fit three (80 registers, <= 75 KB shared)
+// resident blocks per SM the launch bounds ask for.  Round 1 ran the fp32 kernels without injected draws at three (80 registers);
+// with the EVM guard and its replay call they need more than 80 registers (spills made three blocks 2x slower than two).
 static_assert(sizeof(StreamStage<false>) % 16 == 0 && sizeof(StreamStage<true>) % 16 == 0 && sizeof(StreamWarp<false>) % 16 == 0, "stage alignment");
 #ifndef OFDM_FAST_STREAM_BLOCKS
-#define OFDM_FAST_STREAM_BLOCKS 3       // A/B knob (tools/ab.sh): resident blocks per SM of the fast kernels without injected draws
+#define OFDM_FAST_STREAM_BLOCKS 2       // A/B knob (tools/ab.sh): resident blocks per SM of the fast kernels without injected draws
 #endif
 template <int ARITH, int NOISE> constexpr int stream_blocks_per_sm() { return (ARITH == kArithFast && NOISE != kNoiseInject) ? OFDM_FAST_STREAM_BLOCKS : 2; }
 
@@ -878,7 +884,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
                 if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay exactly
                     const uint2 r = stream_frame_replay<NOISE>(p.in + f * len, NOISE == kNoiseInject ? p.g + f * len : nullptr,
                                                                p.tx_bits + f * 6, sigma_d, p.seed, p.stream, p.frame0 + (uint64_t)f,
-                                                               ws.tile, &ws.lts[0][0]);
+                                                               ws.tile, &ws.lts[0][0], p.replayed);
                     pk = r.x; f_e2 = __uint_as_float(r.y);
                 }
             } else {
@@ -955,6 +961,7 @@ __device__ __forceinline__ SweepLane make_sweep_lane(int u)
 struct SweepFrame {                 // one frame's inputs
     const float2 *x; const float *g; const uint32_t *bits;
     int n_sym; double sigma_d; uint32_t seed, stream; uint64_t frame_id;
+    unsigned long long *replayed;
 };
 struct SweepTotals { uint32_t i, q, both; float e2; };
 
@@ -969,6 +976,7 @@ __device__ __noinline__ SweepTotals sweep_frame_replay(SweepFrame fr, float2 *ti
     const int n_sym = fr.n_sym;
     const int n_pass = 1 + (n_sym > 2 ? (n_sym + 1) / 4 : 0);
     SweepTotals t = {0u, 0u, 0u, 0.f};
+    unsigned long long *replayed = fr.replayed;
     for (int pass = 0; pass < n_pass; ++pass) {
         const int sym = pass == 0 ? grp - 2 : 2 + (pass - 1) * 4 + grp;     // < 0: LTS half
         const bool active = sym < n_sym;
@@ -1016,7 +1024,7 @@ __device__ __noinline__ SweepTotals sweep_frame_replay(SweepFrame fr, float2 *ti
         }
         __syncwarp();
     }
-    if (lane == 0) atomicAdd(&g_replayed_frames, 1ull);
+    if (lane == 0 && replayed != nullptr) atomicAdd(replayed, 1ull);
     return t;
 }
 
@@ -1236,7 +1244,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                 if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions: replay the frame exactly
                     SweepFrame fr;
                     fr.x = p.in + f * len; fr.g = NOISE == kNoiseInject ? p.g + f * len : nullptr; fr.bits = fbits; fr.n_sym = n_sym;
-                    fr.sigma_d = sigma_d; fr.seed = p.seed; fr.stream = p.stream; fr.frame_id = p.frame0 + (uint64_t)f;
+                    fr.sigma_d = sigma_d; fr.seed = p.seed; fr.stream = p.stream; fr.frame_id = p.frame0 + (uint64_t)f; fr.replayed = p.replayed;
                     const SweepTotals t = sweep_frame_replay<NOISE>(fr, ws.tile, &ws.lts[0][0]);
                     f_i = t.i; f_q = t.q; f_both = t.both; f_e2 = t.e2;
                 }

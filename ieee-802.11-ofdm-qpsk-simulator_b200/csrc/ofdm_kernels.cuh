@@ -320,6 +320,7 @@ struct RxParams {
     uint32_t seed, stream;
     uint64_t frame0;
     ofdm_counters *counters;
+    unsigned long long *replayed;   // the context's count of exactly replayed frames (speculating kernels)
     ofdm_rx_dump dump;
 };
 

@@ -36,6 +36,7 @@ struct SweepParams {
     float radius_scale;             // kRadius, or infinity: every (frame, SNR point) is replayed exactly
     float snr_lin[kMaxSnr];         // (float)pow(10, snr/10), OFDM.c:645
     ofdm_counters *counters;        // [n_snr], accumulated into
+    unsigned long long *replayed;   // the context's count of exactly replayed (frame, SNR point)s
 };
 
 struct alignas(16) SweepWarp {
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions / EVM: replay exactly
                 const double sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si]));
                 const uint2 r = stream_frame_replay<kNoiseInject>(p.in + f * len, p.g + f * len, wb, sigma_d, 0u, 0u, 0ull,
-                                                                  ws.tile, &ws.fx[0][0]);
+                                                                  ws.tile, &ws.fx[0][0], p.replayed);
                 pk = r.x; e2 = __uint_as_float(r.y);
             }
             pk_pend = __reduce_add_sync(0xffffffffu, pk);           // one REDUX: the three 8-bit fields stay below 97

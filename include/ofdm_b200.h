@@ -108,7 +108,8 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *                       = 1  frames staged in HBM (TX, fading, power, one receiver kernel per SNR point);
  *                       = 2  the fused on-chip kernel; both give the same totals */
 int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value);
-/* frames the speculating EXACT kernels replayed in the reference's arithmetic since start / the last reset (per process) */
+/* frames (sweeps: frame x SNR points) the speculating kernels of THIS context replayed in the reference's arithmetic since
+ * its creation / the last reset */
 int ofdm_ctx_replayed_frames(ofdm_ctx *ctx, uint64_t *count, int reset);
 int ofdm_ctx_sm_count(const ofdm_ctx *ctx);
 uint64_t ofdm_ctx_launch_count(const ofdm_ctx *ctx);          /* kernels launched so far by this ctx */

@@ -134,8 +134,8 @@ def test_receiver_fast(ofdm, pkg, port, n_sym, snr):
                                  want=("H", "eq", "frame_bit_errors", "frame_evm_lin"))
     assert close_rel(d["H"].cpu().numpy(), want["H"])
     # Per-bin dumps come from the generic kernel, plain fp32 end to end.  Equalised points relative to each frame's peak
-    # magnitude: a bin whose channel estimate is nearly zero amplifies the fp32 transform's error in H, so single frames
-    # deviate by more than 1e-5 (the measured worst figures go to $OFDM_TEST_LOG when set; DESIGN.md section 4 quotes them).
+    # magnitude: a bin whose channel estimate is nearly zero amplifies the fp32 transform's error in H (the measured worst
+    # figures go to $OFDM_TEST_LOG when set; DESIGN.md section 4 quotes them).
     eq, weq = d["eq"].cpu().numpy().astype(np.float64), want["eq"].astype(np.float64)
     scale = np.abs(weq).reshape(n_frames, -1).max(axis=1)[:, None, None]
     worst_eq = np.max(np.abs(eq - weq) / scale)
@@ -143,7 +143,7 @@ def test_receiver_fast(ofdm, pkg, port, n_sym, snr):
     if os.environ.get("OFDM_TEST_LOG"):
         with open(os.environ["OFDM_TEST_LOG"], "a") as f:
             f.write("test_receiver_fast n_sym=%d snr=%.1f worst |eq - ref| / frame peak %.3e, worst per-frame EVM rel %.3e\n" % (n_sym, snr, worst_eq, worst_evm))
-    assert worst_eq <= 20 * REL and worst_evm <= 20 * REL, (worst_eq, worst_evm)
+    assert worst_eq <= REL and worst_evm <= REL, (worst_eq, worst_evm)        # measured on B200: 4.4e-6 / 3.3e-6 at 3 dB, < 1e-6 from 8 dB up
     diff = np.abs(d["frame_bit_errors"].cpu().numpy() - want["bit_errors"])
     assert diff.sum() <= 2          # decisions differ only for rails within fp32 rounding of zero
     # The EVM the path reports (batch totals, streaming kernels) meets the 1e-5 of the north star in FAST mode too: those
