@@ -437,14 +437,15 @@ def run_configs(o, pkg, torch, dist, dev, args, rank, world):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    tot, rounds = pkg.sweep.mc_sweep_until(o, 11, N_SYM, SNRS, pkg.MODE_FAST, 100, 10 ** 9, args.until_round_frames, 0, rank, world)
+    round_frames = args.until_round_frames * world          # a round keeps every GPU busy for the same time as at N = 1
+    tot, rounds = pkg.sweep.mc_sweep_until(o, 11, N_SYM, SNRS, pkg.MODE_FAST, 100, 10 ** 9, round_frames, 0, rank, world)
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     work = sum(t.frames for t in tot)
     out["cfg3_philox_mc"]["until_100_errors_or_1e-7"] = {
-        "seconds": float(dt.item()), "rounds": rounds, "round_frames": args.until_round_frames, "mode": "fast",
+        "seconds": float(dt.item()), "rounds": rounds, "round_frames": round_frames, "mode": "fast",
         "frame_points": int(work), "symbols_per_s": work * N_SYM / float(dt.item()),
         "points": [{"snr_db": s, "bit_errors": int(t.bit_errors), "bits": int(t.bits), "ber": t.bit_errors / t.bits} for s, t in zip(SNRS, tot)],
         "parallelism": "every round's frame range split over %d GPU(s) for every still-active SNR point; one all-reduce per round" % world}
@@ -662,7 +663,7 @@ def main():
     ap.add_argument("--extras", action="store_true", help="also measure configs[2] (streaming) and configs[3] (Philox MC)")
     ap.add_argument("--stream-frames", type=int, default=8_388_608, help="frames for the streaming extra (16 Mi data symbols)")
     ap.add_argument("--mc-frames", type=int, default=2_000_000, help="frames per GPU of the configs[3] / configs[4] Monte-Carlo sweeps")
-    ap.add_argument("--until-round-frames", type=int, default=1 << 20, help="frames per round (all ranks together) of the until-rule sweep")
+    ap.add_argument("--until-round-frames", type=int, default=1 << 20, help="frames per round and GPU of the until-rule sweep")
     ap.add_argument("--no-configs", action="store_true", help="skip configs[2] / [3] / [4] (A/B runs of the headline only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

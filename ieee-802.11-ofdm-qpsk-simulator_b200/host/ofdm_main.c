@@ -20,7 +20,8 @@
  *       has >= E bit errors or >= B bits (default B = E / 1e-7: the BER-1e-7 budget), in rounds of R frames (default 4 Mi);
  *       finished points leave the kernel's SNR list, the others keep their noise streams.  With --gpus N every round's frame
  *       range is split across the GPUs (so the slow high-SNR points use all of them) and the round's counters are all-reduced
- *       (NCCL) before the stop decisions: the result does not depend on the GPU count;
+ *       (NCCL; --round-reduce-host sums the few hundred bytes on the host instead, this being one process) before the stop
+ *       decisions: the result does not depend on the GPU count;
  *   --draws FILE [--bits FILE]: configs[1] from C -- injected-noise sweep (ofdm_sweep_inject_host): FILE holds one float32
  *       standard-normal draw per sample, [frames][160 + 80 nsym] (e.g. the reference's captured g_keep stream); the payload is
  *       the Philox bit stream of --seed, or packed uint32 words [frames][3 nsym] from --bits;
@@ -104,7 +105,7 @@ static void report_rate(const char *what, int n_gpus, long frames, int n_sym, in
 
 /* shard (frame range) across GPUs, counter-based RNG keyed on the global frame index, one all-reduce */
 static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, int n_taps, const float *SNR, int n_snr, int mode, ofdm_counters *totals,
-                           unsigned long long target_errors, unsigned long long max_bits, long round_frames)
+                           unsigned long long target_errors, unsigned long long max_bits, long round_frames, int round_reduce_host)
 {
     ofdm_ctx *ctxs[8] = {0};
     ofdm_ctx *ctx = NULL;
@@ -148,18 +149,32 @@ static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, in
                 CHECK(ofdm_memset_dev(ctx, cnt[d], 0, sizeof(ofdm_counters) * (size_t)n_active));
                 CHECK(ofdm_mc_sweep_points_dev(ctx, seed, (uint64_t)rounds * (uint64_t)round_frames + (uint64_t)lo, n, n_sym, n_taps, snr_a, stream_a,
                                                n_active, mode, (ofdm_counters *)cnt[d]));
-                CHECK(ofdm_counters_pack(ctx, (const ofdm_counters *)cnt[d], n_active, (uint64_t *)ints[d], (double *)dbls[d]));
+                if (!round_reduce_host) CHECK(ofdm_counters_pack(ctx, (const ofdm_counters *)cnt[d], n_active, (uint64_t *)ints[d], (double *)dbls[d]));
             }
-            NCHECK(ncclGroupStart());
-            for (int d = 0; d < n_gpus; ++d) {
-                NCHECK(ncclAllReduce(ints[d], ints[d], 5 * (size_t)n_active, ncclUint64, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
-                NCHECK(ncclAllReduce(dbls[d], dbls[d], 3 * (size_t)n_active, ncclDouble, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+            if (round_reduce_host) {
+                /* one process drives every GPU: the round's partial counters (a few hundred bytes per GPU) can also be summed on the host */
+                static ofdm_counters per_gpu[8][64];
+                for (int d = 0; d < n_gpus; ++d) { ctx = ctxs[d]; CHECK(ofdm_memcpy_d2h(ctx, per_gpu[d], cnt[d], sizeof(ofdm_counters) * (size_t)n_active)); }
+                for (int d = 0; d < n_gpus; ++d) { ctx = ctxs[d]; CHECK(ofdm_ctx_sync(ctx)); }
+                memset(part, 0, sizeof part);
+                for (int d = 0; d < n_gpus; ++d)
+                    for (int j = 0; j < n_active; ++j) {
+                        part[j].bit_errors += per_gpu[d][j].bit_errors; part[j].bits += per_gpu[d][j].bits; part[j].frames_in_error += per_gpu[d][j].frames_in_error;
+                        part[j].rail_errors += per_gpu[d][j].rail_errors; part[j].frames += per_gpu[d][j].frames;
+                        part[j].sum_err2 += per_gpu[d][j].sum_err2; part[j].sum_ref2 += per_gpu[d][j].sum_ref2; part[j].sum_evm_lin += per_gpu[d][j].sum_evm_lin;
+                    }
+            } else {
+                NCHECK(ncclGroupStart());
+                for (int d = 0; d < n_gpus; ++d) {
+                    NCHECK(ncclAllReduce(ints[d], ints[d], 5 * (size_t)n_active, ncclUint64, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+                    NCHECK(ncclAllReduce(dbls[d], dbls[d], 3 * (size_t)n_active, ncclDouble, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+                }
+                NCHECK(ncclGroupEnd());
+                ctx = ctxs[0];
+                CHECK(ofdm_counters_unpack(ctx, (ofdm_counters *)cnt[0], n_active, (const uint64_t *)ints[0], (const double *)dbls[0]));
+                CHECK(ofdm_memcpy_d2h(ctx, part, cnt[0], sizeof(ofdm_counters) * (size_t)n_active));
+                for (int d = 0; d < n_gpus; ++d) { ctx = ctxs[d]; CHECK(ofdm_ctx_sync(ctx)); }
             }
-            NCHECK(ncclGroupEnd());
-            ctx = ctxs[0];
-            CHECK(ofdm_counters_unpack(ctx, (ofdm_counters *)cnt[0], n_active, (const uint64_t *)ints[0], (const double *)dbls[0]));
-            CHECK(ofdm_memcpy_d2h(ctx, part, cnt[0], sizeof(ofdm_counters) * (size_t)n_active));
-            for (int d = 0; d < n_gpus; ++d) { ctx = ctxs[d]; CHECK(ofdm_ctx_sync(ctx)); }
             int keep = 0;
             for (int j = 0; j < n_active; ++j) {
                 ofdm_counters *t = &totals[active[j]];
@@ -173,8 +188,8 @@ static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, in
             ++rounds;
         }
         const double dt = now_s() - t0;
-        fprintf(stderr, "until-sweep: %d rounds of %ld frames, %llu frame-points x %d symbols on %d GPU(s) in %.3f s = %.3e data symbols/s\n", rounds,
-                round_frames, done_frames, n_sym, n_gpus, dt, (double)done_frames * n_sym / dt);
+        fprintf(stderr, "until-sweep: %d rounds of %ld frames, %llu frame-points x %d symbols on %d GPU(s) in %.3f s = %.3e data symbols/s (round totals: %s)\n", rounds,
+                round_frames, done_frames, n_sym, n_gpus, dt, (double)done_frames * n_sym / dt, round_reduce_host ? "summed on the host" : "NCCL all-reduce");
         for (int d = 0; d < n_gpus; ++d) {
             ncclCommDestroy(comms[d]);
             ofdm_dev_free(ctxs[d], cnt[d]); ofdm_dev_free(ctxs[d], ints[d]); ofdm_dev_free(ctxs[d], dbls[d]);
@@ -225,11 +240,13 @@ int main(int argc, char **argv)
     unsigned long long target_errors = 0, max_bits = 0;
     long round_frames = 1L << 22;
     const char *draws_file = NULL, *bits_file = NULL;
+    int round_reduce_host = 0;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
         if (!strcmp(a, "--quiet")) { quiet = 1; continue; }
         if (!strcmp(a, "--stage-chain")) { full_chain = 0; continue; }
         if (!strcmp(a, "--full-chain")) { full_chain = 1; continue; }
+        if (!strcmp(a, "--round-reduce-host")) { round_reduce_host = 1; continue; }
         if (!v) { fprintf(stderr, "missing value for %s\n", a); return 2; }
         if (!strcmp(a, "--message")) message = v;
         else if (!strcmp(a, "--frames")) frames = atol(v);
@@ -264,7 +281,7 @@ int main(int argc, char **argv)
     if (n_gpus > 1) {
 #ifdef OFDM_WITH_NCCL
         if (frames < 2 && target_errors == 0) { fprintf(stderr, "--gpus needs --frames N > 1 or --target-errors E\n"); return 2; }
-        int rc = sweep_multi_gpu(n_gpus, seed, frames, n_sym, n_taps, SNR, n_snr, mode, totals, target_errors, max_bits, round_frames);
+        int rc = sweep_multi_gpu(n_gpus, seed, frames, n_sym, n_taps, SNR, n_snr, mode, totals, target_errors, max_bits, round_frames, round_reduce_host);
         if (rc) return rc;
 #else
         fprintf(stderr, "built without NCCL (make ofdm_sweep NCCL=1)\n");
