@@ -25,6 +25,7 @@ struct ofdm_ctx {
     bool force_replay = false;       // testing knob: the verification fails every frame
     bool general_stream = false;     // testing knob: two-symbol frames through the multi-pass streaming kernel too
     bool fused_sweep = true;         // ofdm_sweep_inject_*: the all-SNR kernel k_sweep_lin (default frame shape) instead of one launch per SNR point
+    float evm_guard = kEvmGuard;     // tuning knob: bins with |H| below this many error radii are replayed exactly (EVM accuracy vs replays)
     int multipath_path = 0;          // configs[4]: 0 = auto (fast: fused on-chip kernel, exact: HBM-staged frames), 1 = staged, 2 = fused
     char err[256] = {0};
     float lts_freq[128];
@@ -214,6 +215,7 @@ int launch_stream_n(ofdm_ctx *ctx, const RxParams &p)
 void set_radius(ofdm_ctx *ctx, RxParams &q)
 {
     q.replayed = ctx->replayed_dev;
+    q.evm_guard = ctx->evm_guard;
     q.radius_scale = ctx->force_replay ? INFINITY : kRadius;
     q.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf((float)OFDM_FRAME_LEN(q.n_sym) * q.snr_lin) * 1.001f;
 }
@@ -450,6 +452,7 @@ int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "force_generic_rx")) { ctx->force_generic = value != 0; return OFDM_OK; }
     if (!strcmp(name, "exact_speculation")) { ctx->checked = value != 0; return OFDM_OK; }
     if (!strcmp(name, "force_replay")) { ctx->force_replay = value != 0; return OFDM_OK; }
+    if (!strcmp(name, "evm_guard")) { if (value < 1 || value > 65536) return fail(ctx, OFDM_ERR_INVALID, "evm_guard: 1..65536 radii"); ctx->evm_guard = (float)value; return OFDM_OK; }
     if (!strcmp(name, "fused_sweep")) { ctx->fused_sweep = value != 0; return OFDM_OK; }
     if (!strcmp(name, "general_stream")) { ctx->general_stream = value != 0; return OFDM_OK; }
     if (!strcmp(name, "multipath_path")) { if (value < 0 || value > 2) return fail(ctx, OFDM_ERR_INVALID, "multipath_path: 0..2"); ctx->multipath_path = value; return OFDM_OK; }
@@ -913,6 +916,7 @@ int sweep_points(ofdm_ctx *ctx, const float *frames, const float *g, const float
         for (int i = 0; i < p.n_snr; ++i) p.snr_lin[i] = snr_linear(snr_db[s0 + i]);
         p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
         p.replayed = ctx->replayed_dev;
+        p.evm_guard = ctx->evm_guard;
         p.counters = counters + s0;
         for (long f0 = 0; f0 < n_frames; f0 += max_frames) {
             p.n_frames = n_frames - f0 < max_frames ? n_frames - f0 : max_frames;
@@ -968,6 +972,7 @@ int mc_awgn_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, i
             }
             p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
             p.replayed = ctx->replayed_dev;
+            p.evm_guard = ctx->evm_guard;
             p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
             auto launch = [&](auto k) -> int {
                 OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1153,6 +1158,7 @@ int mc_multipath_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_fram
             }
             p.radius_scale = ctx->force_replay ? INFINITY : kRadius;
             p.replayed = ctx->replayed_dev;
+            p.evm_guard = ctx->evm_guard;
             p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
             auto launch = [&](auto k) -> int {
                 OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -173,6 +173,7 @@ struct McParams {
     uint32_t stream[kMaxSnr];       // Philox noise stream of each point (the index of the SNR point in the caller's full list)
     float radius_scale;             // kArithChecked: kRadius, or infinity to replay every point
     float radius_chan;              // kArithChecked: kChanRadius * sqrt(320) (times sqrt(P) = the channel term), or infinity
+    float evm_guard;                // EVM guard in radii (kEvmGuard; option "evm_guard")
     int n_taps;                     // multipath variant: taps per frame (1..kMaxTaps)
     ofdm_counters *counters;        // [n_snr], accumulated into
     unsigned long long *replayed;   // the context's count of exactly replayed (frame, SNR point)s
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_mc_philox(McParams p)
                 const float rA = __shfl_sync(0xffffffffu, rad, 0), rB = __shfl_sync(0xffffffffu, rad, 8);
                 const float r0 = __shfl_sync(0xffffffffu, rad, 16), r1 = __shfl_sync(0xffffffffu, rad, 24);
                 const float rH2 = rA + rB;                                        // 2 r_H
-                const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
+                const float den_min4 = (p.evm_guard * rH2) * (p.evm_guard * rH2);
                 bool doubt = false;
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
@@ -869,7 +870,7 @@ __global__ void __launch_bounds__(kThreads, stream_blocks_per_sm<ARITH, NOISE>()
                 float2 e2v = make_float2(0.f, 0.f);
                 const float4 rad = *reinterpret_cast<const float4 *>(ws.radius);
                 const float rH2 = rad.x + rad.y;                                  // 2 r_H
-                const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
+                const float den_min4 = (p.evm_guard * rH2) * (p.evm_guard * rH2);
                 bool doubt = false;
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
@@ -1178,7 +1179,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                         r4 = *reinterpret_cast<const float4 *>(ws.radius);
                         rH2 = r4.x + r4.y;                                        // 2 r_H, kept for the frame's later passes
                     }
-                    const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
+                    const float den_min4 = (p.evm_guard * rH2) * (p.evm_guard * rH2);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         const int isym = ic.f_off[t] < kWin ? 0 : 1;              // the item's symbol
@@ -1210,7 +1211,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream_rxn(RxParams p)
                     __syncwarp();
                     float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (SPEC) r4 = *reinterpret_cast<const float4 *>(ws.radius);
-                    const float den_min4 = (kEvmGuard * rH2) * (kEvmGuard * rH2);
+                    const float den_min4 = (p.evm_guard * rH2) * (p.evm_guard * rH2);
 #pragma unroll
                     for (int round = 0; round < 2; ++round) {
 #pragma unroll

@@ -317,6 +317,7 @@ struct RxParams {
     float snr_lin;
     float radius_scale;         // kArithChecked: error-radius factor (kRadius; infinity forces every frame to be replayed)
     float radius_chan;          // kArithChecked: kChanRadius * sqrt(frame_len * snr_lin): times sigma = the speculated channel's share
+    float evm_guard;            // EVM guard in radii (kEvmGuard; option "evm_guard")
     uint32_t seed, stream;
     uint64_t frame0;
     ofdm_counters *counters;

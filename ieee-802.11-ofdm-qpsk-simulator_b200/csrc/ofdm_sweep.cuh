@@ -34,6 +34,7 @@ struct SweepParams {
     long n_frames;
     int n_snr;
     float radius_scale;             // kRadius, or infinity: every (frame, SNR point) is replayed exactly
+    float evm_guard;                // EVM guard in radii (kEvmGuard; option "evm_guard")
     float snr_lin[kMaxSnr];         // (float)pow(10, snr/10), OFDM.c:645
     ofdm_counters *counters;        // [n_snr], accumulated into
     unsigned long long *replayed;   // the context's count of exactly replayed (frame, SNR point)s
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             const float sg = __shfl_sync(0xffffffffu, si < 32 ? sig_lo : sig_hi, si & 31);
             const float2 sg2 = make_float2(sg, sg);
             const float rH2 = fmaf(sg, rHN, rHX);
-            const float gd = kEvmGuard * rH2, den_min4 = gd * gd;
+            const float gd = p.evm_guard * rH2, den_min4 = gd * gd;
             float2 e2v = make_float2(0.f, 0.f);
             uint32_t pk = 0;
             bool doubt = false;

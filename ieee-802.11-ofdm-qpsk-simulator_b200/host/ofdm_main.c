@@ -20,8 +20,8 @@
  *       has >= E bit errors or >= B bits (default B = E / 1e-7: the BER-1e-7 budget), in rounds of R frames (default 4 Mi);
  *       finished points leave the kernel's SNR list, the others keep their noise streams.  With --gpus N every round's frame
  *       range is split across the GPUs (so the slow high-SNR points use all of them) and the round's counters are all-reduced
- *       (NCCL; --round-reduce-host sums the few hundred bytes on the host instead, this being one process) before the stop
- *       decisions: the result does not depend on the GPU count;
+ *       before the stop decisions -- summed on the host by default (this is one process driving every GPU; the partial counters are a
+ *       few hundred bytes), or with NCCL all-reduces (--round-reduce-nccl): the result does not depend on the GPU count;
  *   --draws FILE [--bits FILE]: configs[1] from C -- injected-noise sweep (ofdm_sweep_inject_host): FILE holds one float32
  *       standard-normal draw per sample, [frames][160 + 80 nsym] (e.g. the reference's captured g_keep stream); the payload is
  *       the Philox bit stream of --seed, or packed uint32 words [frames][3 nsym] from --bits;
@@ -240,13 +240,15 @@ int main(int argc, char **argv)
     unsigned long long target_errors = 0, max_bits = 0;
     long round_frames = 1L << 22;
     const char *draws_file = NULL, *bits_file = NULL;
-    int round_reduce_host = 0;
+    int round_reduce_host = 1;           /* until rule: per-round totals summed on the host (measured 8 GPUs, 13 rounds: 0.033 s against 0.294 s with two
+                                            single-process NCCL group all-reduces per round, profiles/r2_c_driver_until_8gpu.txt) */
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
         if (!strcmp(a, "--quiet")) { quiet = 1; continue; }
         if (!strcmp(a, "--stage-chain")) { full_chain = 0; continue; }
         if (!strcmp(a, "--full-chain")) { full_chain = 1; continue; }
         if (!strcmp(a, "--round-reduce-host")) { round_reduce_host = 1; continue; }
+        if (!strcmp(a, "--round-reduce-nccl")) { round_reduce_host = 0; continue; }
         if (!v) { fprintf(stderr, "missing value for %s\n", a); return 2; }
         if (!strcmp(a, "--message")) message = v;
         else if (!strcmp(a, "--frames")) frames = atol(v);

@@ -102,6 +102,8 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *                            both give the same error counts)
  *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path)
  *   "general_stream"    = 1  two-symbol frames also take the multi-pass streaming kernel that serves every other frame shape
+ *   "evm_guard"         = N  bins whose channel estimate is smaller than N error radii are replayed exactly (default 512): the
+ *                            EVM sums' distance from the all-exact kernel's against the number of replays
  *   "fused_sweep"       = 0  injected-noise sweeps launch one channel+receiver kernel per SNR point instead of the all-SNR
  *                            kernel (default 1; same totals)
  *   "multipath_path"    = 0  ofdm_mc_sweep_multipath_dev picks the faster of its two implementations per mode (default);

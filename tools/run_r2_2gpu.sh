@@ -25,8 +25,8 @@ mkdir -p /tmp/d1 /tmp/dN /tmp/dH
 for G in 1 $N; do
   ./ofdm_sweep --quiet --outdir /tmp/d$([ $G = 1 ] && echo 1 || echo N) --gpus $G --target-errors 100 --max-bits 10000000000 --round-frames 4194304 --snr-start 0 --snr-count 21 --mode fast --seed 3 2>&1 | grep -v "NCCL version"
 done 2>&1 | tee $GRAFT_REPO_ROOT/gpurun_out/r2_c_driver_until_${N}gpu.txt
-./ofdm_sweep --quiet --outdir /tmp/dH --gpus $N --round-reduce-host --target-errors 100 --max-bits 10000000000 --round-frames 4194304 --snr-start 0 --snr-count 21 --mode fast --seed 3 2>&1 | grep -v "NCCL version" | tee -a $GRAFT_REPO_ROOT/gpurun_out/r2_c_driver_until_${N}gpu.txt
-./ofdm_sweep --quiet --outdir /tmp/dH --gpus $N --target-errors 100 --max-bits 10000000000 --round-frames 33554432 --snr-start 0 --snr-count 21 --mode fast --seed 3 2>&1 | grep -v "NCCL version" | tee -a $GRAFT_REPO_ROOT/gpurun_out/r2_c_driver_until_${N}gpu.txt
+./ofdm_sweep --quiet --outdir /tmp/dH --gpus $N --round-reduce-nccl --target-errors 100 --max-bits 10000000000 --round-frames 4194304 --snr-start 0 --snr-count 21 --mode fast --seed 3 2>&1 | grep -v "NCCL version" | tee -a $GRAFT_REPO_ROOT/gpurun_out/r2_c_driver_until_${N}gpu.txt
+./ofdm_sweep --quiet --outdir /tmp/dH --gpus $N --round-reduce-nccl --target-errors 100 --max-bits 10000000000 --round-frames 33554432 --snr-start 0 --snr-count 21 --mode fast --seed 3 2>&1 | grep -v "NCCL version" | tee -a $GRAFT_REPO_ROOT/gpurun_out/r2_c_driver_until_${N}gpu.txt
 cmp /tmp/d1/Output_BER.txt /tmp/dN/Output_BER.txt && cmp /tmp/d1/Output_EVM_AGC.txt /tmp/dN/Output_EVM_AGC.txt && echo "until-rule result files identical for 1 and $N GPUs" | tee -a $GRAFT_REPO_ROOT/gpurun_out/r2_c_driver_until_${N}gpu.txt
 cat /tmp/dN/Output_BER.txt >> $GRAFT_REPO_ROOT/gpurun_out/r2_c_driver_until_${N}gpu.txt
 # fixed-size sweeps, weak scaling (16 M frames per GPU), configs[3] and configs[4]
