@@ -226,6 +226,7 @@ int launch_stream_n_mode(ofdm_ctx *ctx, int mode, const RxParams &p)
     if (mode == OFDM_MODE_EXACT && !ctx->checked) return launch_stream_n<kArithExact, NOISE>(ctx, p);
     RxParams q = p;
     set_radius(ctx, q);                 // fast mode keeps the EVM guard (tiny |H| bins are replayed exactly), exact mode verifies every decision
+    if (mode != OFDM_MODE_EXACT && NOISE == kNoisePhilox) q.evm_guard = 0.f;      // statistical results: plain fp32 (see launch_rx_any)
     if (mode != OFDM_MODE_EXACT) return launch_stream_n<kArithFast, NOISE>(ctx, q);
     return launch_stream_n<kArithChecked, NOISE>(ctx, q);
 }
@@ -260,6 +261,7 @@ int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
         set_radius(ctx, q);             // the EVM guard of the fast kernels
         if (noise == kNoiseNone) return launch_stream<kArithFast, kNoiseNone>(ctx, q);
         if (noise == kNoiseInject) return launch_stream<kArithFast, kNoiseInject>(ctx, q);
+        q.evm_guard = 0.f;              // Philox noise: statistical results, plain fp32 like the fused Monte-Carlo kernel
         return launch_stream<kArithFast, kNoisePhilox>(ctx, q);
     }
     if (mode == OFDM_MODE_EXACT) {
