@@ -6,6 +6,8 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <set>
+#include <utility>
 
 #include "ofdm_chain.cuh"
 #include "ofdm_sweep.cuh"
@@ -77,6 +79,20 @@ int bind(ofdm_ctx *ctx)
     if (!ctx) return OFDM_ERR_INVALID;
     OFDM_CUDA(ctx, cudaSetDevice(ctx->device));
     return OFDM_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set once per (kernel, device), not per launch
+template <typename K>
+cudaError_t allow_smem(ofdm_ctx *ctx, K kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<const void *, int> key(reinterpret_cast<const void *>(kernel), ctx->device);
+    if (done.count(key)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done.insert(key);
+    return e;
 }
 
 // persistent launch geometry: resident blocks per SM (from the occupancy calculator) x SM count,
@@ -195,7 +211,7 @@ int launch_stream(ofdm_ctx *ctx, const RxParams &p)
 {
     auto k = k_stream_rx2<ARITH, NOISE>;
     const size_t smem = stream_smem_bytes<NOISE>();
-    OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
     int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
     k<<<grid, kThreads, smem, ctx->stream>>>(p);
     return check_launch(ctx, "k_stream_rx2");
@@ -206,7 +222,7 @@ int launch_stream_n(ofdm_ctx *ctx, const RxParams &p)
 {
     auto k = k_stream_rxn<ARITH, NOISE>;
     const size_t smem = stream_smem_bytes<NOISE>();
-    OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
     int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
     k<<<grid, kThreads, smem, ctx->stream>>>(p);
     return check_launch(ctx, "k_stream_rxn");
@@ -621,7 +637,7 @@ int ofdm_tx_frames(ofdm_ctx *ctx, const uint32_t *bits, float *frames, float *po
         // default frame shape: frames leave shared memory through the TMA engine (k_tx_frames2)
         const size_t smem = tx2_smem_bytes();
         auto launch = [&](auto k) -> int {
-            OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
             int grid = grid_for(ctx, k, smem, kWarpsPerBlock * 2, n_frames);
             k<<<grid, kThreads, smem, ctx->stream>>>(bits, reinterpret_cast<float2 *>(frames), n_frames);
             return check_launch(ctx, "k_tx_frames2");
@@ -927,7 +943,7 @@ int sweep_points(ofdm_ctx *ctx, const float *frames, const float *g, const float
             p.power = power + f0;
             p.tx_bits = bits + f0 * 6;
             auto launch = [&](auto k) -> int {
-                OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
                 int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
                 k<<<grid, kThreads, smem, ctx->stream>>>(p);
                 return check_launch(ctx, "k_sweep_lin");
@@ -977,7 +993,7 @@ int mc_awgn_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, i
             p.evm_guard = ctx->evm_guard;
             p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
             auto launch = [&](auto k) -> int {
-                OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
                 int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
                 k<<<grid, kThreads, smem, ctx->stream>>>(p);
                 return check_launch(ctx, "k_mc_philox");
@@ -1105,11 +1121,11 @@ static int multipath_common(ofdm_ctx *ctx, bool philox, const float *tx, const f
     const float2 *x = reinterpret_cast<const float2 *>(tx), *h = reinterpret_cast<const float2 *>(taps);
     float2 *y = reinterpret_cast<float2 *>(out), *ho = reinterpret_cast<float2 *>(taps_out);
     if (philox) {
-        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
+        if (smem > 48 * 1024) OFDM_CUDA(ctx, allow_smem(ctx, k_multipath<true>, fir_smem_bytes(kFirTile)));
         int grid = grid_for(ctx, k_multipath<true>, smem, kWarpsPerBlock, n_frames);
         k_multipath<true><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len, tile);
     } else {
-        if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_multipath<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
+        if (smem > 48 * 1024) OFDM_CUDA(ctx, allow_smem(ctx, k_multipath<false>, fir_smem_bytes(kFirTile)));
         int grid = grid_for(ctx, k_multipath<false>, smem, kWarpsPerBlock, n_frames);
         k_multipath<false><<<grid, kThreads, smem, ctx->stream>>>(x, h, seed, frame0, n_taps, y, ho, n_frames, len, tile);
     }
@@ -1163,7 +1179,7 @@ int mc_multipath_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_fram
             p.evm_guard = ctx->evm_guard;
             p.radius_chan = ctx->force_replay ? INFINITY : kChanRadius * sqrtf(320.f) * 1.001f;
             auto launch = [&](auto k) -> int {
-                OFDM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
                 int grid = grid_for(ctx, k, smem, kWarpsPerBlock, p.n_frames);
                 k<<<grid, kThreads, smem, ctx->stream>>>(p);
                 return check_launch(ctx, "k_mc_philox<multipath>");
@@ -1212,7 +1228,7 @@ int ofdm_rrc_tx(ofdm_ctx *ctx, const float *frames, float *out, long n_frames, i
     OFDM_REQUIRE(ctx, frames != nullptr && out != nullptr && frames != out);
     const int tile = fir_tile(frame_len);
     const size_t smem = fir_smem_bytes(tile);
-    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_tx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, allow_smem(ctx, k_rrc_tx, fir_smem_bytes(kFirTile)));
     int grid = grid_for(ctx, k_rrc_tx, smem, kWarpsPerBlock, n_frames);
     k_rrc_tx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), reinterpret_cast<float2 *>(out), n_frames, frame_len, tile);
     return check_launch(ctx, "k_rrc_tx");
@@ -1227,7 +1243,7 @@ int ofdm_rrc_rx(ofdm_ctx *ctx, const float *in, float *out, long n_frames, int i
     OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && in != out);
     const int tile = fir_tile(2 * frame_len);
     const size_t smem = fir_smem_bytes(tile);
-    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, allow_smem(ctx, k_rrc_rx, fir_smem_bytes(kFirTile)));
     int grid = grid_for(ctx, k_rrc_rx, smem, kWarpsPerBlock, n_frames);
     k_rrc_rx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), nullptr, packet_idx, reinterpret_cast<float2 *>(out), n_frames,
                                                    in_len, frame_len, tile);
@@ -1265,7 +1281,7 @@ int ofdm_packet_detect(ofdm_ctx *ctx, const float *rx, float *corr, long n, int 
     int tile = (len - 47 + 31) & ~31;
     if (tile > 4096) tile = 4096;
     const size_t smem = (size_t)(tile + 48) * (sizeof(double) + sizeof(float2));
-    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_packet_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((4096 + 48) * 16)));
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, allow_smem(ctx, k_packet_detect, ((4096 + 48) * 16)));
     int grid = grid_for(ctx, k_packet_detect, smem, 1, n);                  // one capture per block iteration, all resident blocks
     k_packet_detect<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(rx), corr, n, len, tile);
     return check_launch(ctx, "k_packet_detect");
@@ -1318,7 +1334,7 @@ int ofdm_rrc_rx_idx(ofdm_ctx *ctx, const float *in, const int32_t *idx, float *o
     OFDM_REQUIRE(ctx, in != nullptr && out != nullptr && idx != nullptr && in != out);
     const int tile = fir_tile(2 * frame_len);
     const size_t smem = fir_smem_bytes(tile);
-    if (smem > 48 * 1024) OFDM_CUDA(ctx, cudaFuncSetAttribute(k_rrc_rx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fir_smem_bytes(kFirTile)));
+    if (smem > 48 * 1024) OFDM_CUDA(ctx, allow_smem(ctx, k_rrc_rx, fir_smem_bytes(kFirTile)));
     int grid = grid_for(ctx, k_rrc_rx, smem, kWarpsPerBlock, n_frames);
     k_rrc_rx<<<grid, kThreads, smem, ctx->stream>>>(reinterpret_cast<const float2 *>(in), idx, 0, reinterpret_cast<float2 *>(out), n_frames, in_len, frame_len, tile);
     return check_launch(ctx, "k_rrc_rx(idx)");

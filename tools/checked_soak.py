@@ -21,6 +21,7 @@ for seed in range(seeds):
     if seed % 3 == 1:
         frames *= 2.0 ** (seed + 3)            # exact rescaling of the waveform; the power follows
         o._check(lib.ofdm_frame_power(h, frames.data_ptr(), power.data_ptr(), n, 320, pkg.MODE_EXACT))
+    exact_by_snr = []
     for snr in snrs:
         res = []
         for spec in (1, 0):
@@ -30,12 +31,34 @@ for seed in range(seeds):
                                              pkg.MODE_EXACT, cnt.data_ptr(), None))
             res.append((cnt.cpu().numpy().reshape(-1).copy(), o.replayed_frames()))
         a, b = res[0][0], res[1][0]
+        exact_by_snr.append(b)
         same = bool((a[:5] == b[:5]).all())
         decisions += n * 192; replays += res[0][1]; mismatches += 0 if same else 1
         e2a, e2b = a.view(np.float64)[5], b.view(np.float64)[5]
         print("seed %d snr %5.1f: bit errors %11d  replayed %7d (%.3f%%)  totals equal %s  sum_err2 rel diff %.1e"
               % (seed, snr, int(a[0]), res[0][1], 100.0 * res[0][1] / n, same, abs(e2a / e2b - 1)), flush=True)
+    # the all-SNR kernel (k_sweep_lin: one transform per window, a multiply-add per SNR point) against the same all-exact totals
+    o.set_option("exact_speculation", 1)
+    sw = o.new_counters(len(snrs)); o.replayed_frames(reset=True)
+    snr_arr = np.ascontiguousarray(snrs, dtype=np.float32)
+    o._check(lib.ofdm_awgn_rx_inject_sweep(h, frames.data_ptr(), g.data_ptr(), power.data_ptr(), bits.data_ptr(), snr_arr.ctypes.data, len(snrs), n, 2,
+                                           pkg.MODE_EXACT, sw.data_ptr()))
+    swn = sw.cpu().numpy(); rp = o.replayed_frames()
+    same = all(bool((swn[i][:5] == exact_by_snr[i][:5]).all()) for i in range(len(snrs)))
+    worst = max(abs(swn[i].view(np.float64)[5] / exact_by_snr[i].view(np.float64)[5] - 1) for i in range(len(snrs)))
+    decisions += n * 192 * len(snrs); replays += rp; mismatches += 0 if same else 1
+    print("seed %d all-SNR kernel: %d points replayed (%.3f%%)  totals equal at all %d SNR points %s  worst sum_err2 rel diff %.1e"
+          % (seed, rp, 100.0 * rp / (n * len(snrs)), len(snrs), same, worst), flush=True)
 print("decisions compared: %.3e  launches with different totals: %d  replayed frames: %d" % (decisions, mismatches, replays))
+# the fused Monte-Carlo kernel, speculating vs all-exact, on the same Philox streams
+for seed in range(seeds):
+    res = []
+    for spec in (1, 0):
+        o.set_option("exact_speculation", spec); o.replayed_frames(reset=True)
+        c = o.mc_sweep_philox(500 + seed, 0, n, 2, [float(s) for s in range(0, 21)], pkg.MODE_EXACT)
+        res.append(([(x.bit_errors, x.bits, x.frames_in_error, x.rail_errors, x.frames) for x in c], [x.sum_err2 for x in c], o.replayed_frames()))
+    print("Monte-Carlo seed %d: %d frames x 21 SNR points, replayed %d (%.2f%%), totals equal %s, worst sum_err2 rel diff %.1e"
+          % (seed, n, res[0][2], 100.0 * res[0][2] / (n * 21), res[0][0] == res[1][0], max(abs(a / b - 1) for a, b in zip(res[0][1], res[1][1]))), flush=True)
 
 # the same comparison on fading channels (configs[4]: 8 random taps per frame, on-chip Philox noise, HBM-staged path) and on
 # other frame shapes (multi-pass streaming receiver)
