@@ -126,7 +126,9 @@ constexpr float kEvmGuard = 512.f;
 // is recovered with k = 4 sc = 1 / sc ... E = F conj(G) / |G|^2 * k; the sign of sc joins the sign comparison.
 // LEVEL 2: decisions and EVM guard verified (kArithChecked).  LEVEL 1: EVM guard only -- what the fast kernels of round 2 use
 // so that their EVM sums stay within 1e-5 of the reference's too (the rare frames with a tiny |H| bin are replayed exactly).
-template <int LEVEL>
+// THR_GIVEN: the caller supplies the decision threshold (rF carries it; rH2 unused) -- the sweep kernel evaluates it as a
+// polynomial in sigma per item instead of from |F|_1 and |G|_1 per point (ofdm_sweep.cuh).
+template <int LEVEL, bool THR_GIVEN = false>
 __device__ __forceinline__ uint32_t process_bin_spec(float2 F, float2 G, float k, uint32_t txp, float rF, float rH2, float den_min4,
                                                      float2 &e2, bool &doubt)
 {
@@ -143,8 +145,12 @@ __device__ __forceinline__ uint32_t process_bin_spec(float2 F, float2 G, float k
     const uint32_t ei_ = (__float_as_uint(sr) ^ sx ^ kb) >> 31, eq_ = (__float_as_uint(si) ^ sq ^ kb) >> 31;
     bool safe;
     if (LEVEL >= 2) {
-        const float fa = fabsf(a) + fabsf(b), hc = fabsf(c) + fabsf(d);
-        const float thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
+        float thr;
+        if (THR_GIVEN) thr = rF;
+        else {
+            const float fa = fabsf(a) + fabsf(b), hc = fabsf(c) + fabsf(d);
+            thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
+        }
         // reference numerator >= 1e-30 in magnitude and reference |H|^2 < 1e14: the float quotient keeps its sign (>= 1e-44)
         safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 2e-30f && den < 1.6e14f && den > den_min4;
     } else {

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
         const float4 rX = *reinterpret_cast<const float4 *>(ws.norm), rN = *reinterpret_cast<const float4 *>(ws.norm + 4);
         const float rHX = rX.x + rX.y, rHN = rN.x + rN.y;                      // 2 r_H = r_A + r_B
         float2 FX[3], FN[3], GX[3], GN[3];
-        float rFX[3], rFN[3];
+        float c0[3], c1[3], c2[3];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const int bin = ic.bin[t];
@@ -165,8 +165,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             FX[t] = (&ws.fx[2][0])[ic.f_off[t]];
             FN[t] = (&ws.fn[2][0])[ic.f_off[t]];
             const bool sym0 = ic.f_off[t] < kWin;                              // the item's symbol
-            rFX[t] = sym0 ? rX.z : rX.w;
-            rFN[t] = sym0 ? rN.z : rN.w;
+            const float rFX = sym0 ? rX.z : rX.w, rFN = sym0 ? rN.z : rN.w;
+            // The decision threshold of process_bin_spec, r_F (|G|_1 + r_H2) + r_H2 |F|_1 + 1.2e-7 |F|_1 |G|_1, as a polynomial in
+            // sigma: with |F|_1 <= |FX|_1 + sigma |FN|_1, |G|_1 <= |GX|_1 + sigma |GN|_1 (triangle inequality) and the radii
+            // r = rX + sigma rN, every factor is a non-negative affine function of sigma, so the products are bounded by
+            // c0 + c1 sigma + c2 sigma^2 -- three coefficients per item and frame, two multiply-adds per SNR point.
+            if (LEVEL >= 2) {
+                const float faX = fabsf(FX[t].x) + fabsf(FX[t].y), faN = fabsf(FN[t].x) + fabsf(FN[t].y);
+                const float hcX = fabsf(GX[t].x) + fabsf(GX[t].y), hcN = fabsf(GN[t].x) + fabsf(GN[t].y);
+                const float A0 = hcX + rHX, A1 = hcN + rHN;
+                c0[t] = fmaf(rFX, A0, fmaf(rHX, faX, 1.2e-7f * (faX * hcX)));
+                c1[t] = fmaf(rFX, A1, fmaf(rFN, A0, fmaf(rHX, faN, fmaf(rHN, faX, 1.2e-7f * fmaf(faX, hcN, faN * hcX)))));
+                c2[t] = fmaf(rFN, A1, fmaf(rHN, faN, 1.2e-7f * (faN * hcN)));
+            } else { c0[t] = c1[t] = c2[t] = 0.f; }
         }
         __syncwarp();                                         // everyone holds its items: fx / fn may be overwritten
         uint32_t txp[3];
@@ -203,8 +214,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             for (int t = 0; t < 3; ++t) {
                 const float2 F = __ffma2_rn(sg2, FN[t], FX[t]);
                 const float2 G = __ffma2_rn(sg2, GN[t], GX[t]);
-                const float rF = fmaf(sg, rFN[t], rFX[t]);
-                pk += process_bin_spec<LEVEL>(F, G, k4[t], txp[t], rF, rH2, den_min4, e2v, doubt);
+                const float thr = fmaf(fmaf(c2[t], sg, c1[t]), sg, c0[t]);
+                pk += process_bin_spec<LEVEL, true>(F, G, k4[t], txp[t], thr, rH2, den_min4, e2v, doubt);
             }
             float e2 = e2v.x + e2v.y;
             if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions / EVM: replay exactly
