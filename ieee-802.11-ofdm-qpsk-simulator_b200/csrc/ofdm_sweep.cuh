@@ -218,7 +218,25 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
                 pk += process_bin_spec<LEVEL, true>(F, G, k4[t], txp[t], thr, rH2, den_min4, e2v, doubt);
             }
             float e2 = e2v.x + e2v.y;
-            if (__any_sync(0xffffffffu, doubt)) {             // not provably the reference's decisions / EVM: replay exactly
+            bool replay = __any_sync(0xffffffffu, doubt);
+            if (LEVEL >= 2 && replay) {
+                // The polynomial is an upper bound of the per-point threshold (triangle inequality): before paying for a replay,
+                // recheck the doubtful point with the threshold of its actual |F|_1, |G|_1 -- a third of them pass.
+                const float4 qX = *reinterpret_cast<const float4 *>(ws.norm), qN = *reinterpret_cast<const float4 *>(ws.norm + 4);
+                bool doubt2 = false;
+                float2 e2w = make_float2(0.f, 0.f);
+                uint32_t pk2 = 0;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float2 F = __ffma2_rn(sg2, FN[t], FX[t]);
+                    const float2 G = __ffma2_rn(sg2, GN[t], GX[t]);
+                    const bool sym0 = ic.f_off[t] < kWin;
+                    const float rF = fmaf(sg, sym0 ? qN.z : qN.w, sym0 ? qX.z : qX.w);
+                    pk2 += process_bin_spec<LEVEL>(F, G, k4[t], txp[t], rF, rH2, den_min4, e2w, doubt2);
+                }
+                replay = __any_sync(0xffffffffu, doubt2);
+            }
+            if (replay) {                                     // not provably the reference's decisions / EVM: replay exactly
                 const double sigma_d = __dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[si]));
                 const uint2 r = stream_frame_replay<kNoiseInject>(p.in + f * len, p.g + f * len, wb, sigma_d, 0u, 0u, 0ull,
                                                                   ws.tile, &ws.fx[0][0], p.replayed);
