@@ -28,6 +28,7 @@ struct ofdm_ctx {
     bool general_stream = false;     // testing knob: two-symbol frames through the multi-pass streaming kernel too
     bool fused_sweep = true;         // ofdm_sweep_inject_*: the all-SNR kernel k_sweep_lin (default frame shape) instead of one launch per SNR point
     float evm_guard = kEvmGuard;     // tuning knob: bins with |H| below this many error radii are replayed exactly (EVM accuracy vs replays)
+    uint32_t power_margin = 16;      // k_frame_power_tiled: samples whose running sum is within this many double ulps of a float tie take the reference's operations
     int multipath_path = 0;          // configs[4]: 0 = auto (fast: fused on-chip kernel, exact: HBM-staged frames), 1 = staged, 2 = fused
     char err[256] = {0};
     float lts_freq[128];
@@ -299,7 +300,11 @@ int frame_power(ofdm_ctx *ctx, const float *frames, float *power, long n_frames,
         const bool vec_ok = ((uintptr_t)frames % 16 == 0) && (len % 2 == 0);
         const bool skip = lts_prefix && vec_ok;
         const float2 *x = reinterpret_cast<const float2 *>(frames);
-        if (vec_ok)
+        const int first = skip ? 160 : 0;
+        if (vec_ok && (len - first) % 16 == 0 && len > first)
+            k_frame_power_tiled<<<(int)((n_frames + 255) / 256), kThreads, 0, ctx->stream>>>(x, power, n_frames, len, first,
+                                                                                           skip ? ctx->lts_power_prefix : 0.0f, ctx->power_margin);
+        else if (vec_ok)
             k_frame_power_exact<true><<<blocks_1d(n_frames), 256, 0, ctx->stream>>>(x, power, n_frames, len, skip ? 160 : 0,
                                                                                   skip ? ctx->lts_power_prefix : 0.0f);
         else
@@ -471,6 +476,7 @@ int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "exact_speculation")) { ctx->checked = value != 0; return OFDM_OK; }
     if (!strcmp(name, "force_replay")) { ctx->force_replay = value != 0; return OFDM_OK; }
     if (!strcmp(name, "evm_guard")) { if (value < 1 || value > 65536) return fail(ctx, OFDM_ERR_INVALID, "evm_guard: 1..65536 radii"); ctx->evm_guard = (float)value; return OFDM_OK; }
+    if (!strcmp(name, "power_margin")) { if (value < 16 || value > (1 << 28)) return fail(ctx, OFDM_ERR_INVALID, "power_margin: 16..2^28 ulps"); ctx->power_margin = (uint32_t)value; return OFDM_OK; }
     if (!strcmp(name, "fused_sweep")) { ctx->fused_sweep = value != 0; return OFDM_OK; }
     if (!strcmp(name, "general_stream")) { ctx->general_stream = value != 0; return OFDM_OK; }
     if (!strcmp(name, "multipath_path")) { if (value < 0 || value > 2) return fail(ctx, OFDM_ERR_INVALID, "multipath_path: 0..2"); ctx->multipath_path = value; return OFDM_OK; }

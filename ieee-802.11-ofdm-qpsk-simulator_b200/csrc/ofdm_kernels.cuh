@@ -194,6 +194,72 @@ __global__ void __launch_bounds__(kThreads) k_frame_power_exact(const float2 *__
     }
     power[f] = __fdiv_rn(p, (float)len);
 }
+// The same chain at memory speed (frames whose summed part is a whole number of 16-sample chunks, i.e. every transmitter
+// frame).  Two changes against k_frame_power_exact, neither visible in the result:
+//  * a warp fetches 32 frames x one 128-byte chunk with coalesced 16-byte loads (four rows per instruction) and turns the
+//    tile through shared memory (row pitch 144 bytes: conflict-free both ways), so every line crosses the chip once and
+//    nothing depends on 2048 threads' lines surviving in L1;
+//  * the term of a sample is speculated as t = fma(x, x, y*y) in double instead of hypot()^2.  glibc's hypot is within one
+//    ulp of sqrt(x^2 + y^2), so its rounded square is within 5 ulps of x^2 + y^2 and t within 1: the two double sums p + term
+//    differ by at most 7 ulps.  They round to the same float unless the speculated sum lies within `margin` (16) double ulps
+//    of a tie between two floats (its low 29 bits next to 2^28) -- 6e-8 of the samples, which take the reference's
+//    operations instead.  The accumulator stays a float-valued double: away from a tie, rounding to float is adding 2^28
+//    to the low word and clearing 29 bits.  Sums outside [1e-30, 1e30] (float subnormals, overflow, NaN) are never speculated.
+//    margin = 2^28 sends every sample through the reference's operations (tests compare the two bit for bit).
+__device__ __forceinline__ double power_step(double pd, float x, float y, uint32_t margin)
+{
+    const double dx = (double)x, dy = (double)y;
+    const double s = __dadd_rn(pd, __fma_rn(dx, dx, __dmul_rn(dy, dy)));
+    const uint32_t lo = (uint32_t)__double2loint(s), hi = (uint32_t)__double2hiint(s);
+    const int dist = (int)(lo & 0x1fffffffu) - 0x10000000;
+    const bool ok = (uint32_t)(dist < 0 ? -dist : dist) > margin && s > 1e-30 && s < 1e30;
+    if (!ok) {                                                      // the reference's operations, OFDM.c:640-641
+        const double h = hypot_glibc(dx, dy);
+        return (double)__double2float_rn(__dadd_rn(pd, __dmul_rn(h, h)));
+    }
+    const uint32_t lo2 = lo + 0x10000000u;
+    return __hiloint2double((int)(hi + (lo2 < lo ? 1u : 0u)), (int)(lo2 & 0xe0000000u));
+}
+constexpr int kPowPitch = 9;                                        // float4 per tile row: 8 data + 1 pad
+__global__ void __launch_bounds__(kThreads) k_frame_power_tiled(const float2 *__restrict__ frames, float *__restrict__ power,
+                                                                long n_frames, int len, int first, float acc0, uint32_t margin)
+{
+    __shared__ float4 s_tile[kWarpsPerBlock][32 * kPowPitch];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long f0 = ((long)blockIdx.x * kWarpsPerBlock + warp) * 32;
+    if (f0 >= n_frames) return;
+    float4 *tile = s_tile[warp];
+    const int col = lane & 7, r0 = lane >> 3;
+    const int n_chunks = (len - first) >> 4, len4 = len >> 1;
+    const float4 *src[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        long f = f0 + 4 * j + r0;
+        f = f < n_frames ? f : n_frames - 1;                        // rows past the end repeat the last frame (not stored)
+        src[j] = reinterpret_cast<const float4 *>(frames) + f * len4 + (first >> 1) + col;
+    }
+    float4 q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = __ldg(src[j]);
+    double pd = (double)acc0;
+    for (int c = 0; c < n_chunks; ++c) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile[(4 * j + r0) * kPowPitch + col] = q[j];
+        __syncwarp();
+        if (c + 1 < n_chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = __ldg(src[j] + 8 * (c + 1));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 v = tile[lane * kPowPitch + k];
+            pd = power_step(pd, v.x, v.y, margin);
+            pd = power_step(pd, v.z, v.w, margin);
+        }
+    }
+    if (f0 + lane < n_frames) power[f0 + lane] = __fdiv_rn((float)pd, (float)len);
+}
 __global__ void __launch_bounds__(kThreads) k_frame_power_fast(const float2 *__restrict__ frames, float *__restrict__ power,
                                                                long n_frames, int len)
 {

@@ -104,6 +104,9 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *   "general_stream"    = 1  two-symbol frames also take the multi-pass streaming kernel that serves every other frame shape
  *   "evm_guard"         = N  bins whose channel estimate is smaller than N error radii are replayed exactly (default 512): the
  *                            EVM sums' distance from the all-exact kernel's against the number of replays
+ *   "power_margin"      = N  the exact frame power speculates each term of the serial float sum as x^2 + y^2 and takes the
+ *                            reference's hypot()^2 where the running sum is within N double ulps of a tie between two floats
+ *                            (default 16, the proven bound is 7; 2^28 = the reference's operations on every sample; same floats)
  *   "fused_sweep"       = 0  injected-noise sweeps launch one channel+receiver kernel per SNR point instead of the all-SNR
  *                            kernel (default 1; same totals)
  *   "multipath_path"    = 0  ofdm_mc_sweep_multipath_dev picks the faster of its two implementations per mode (default);

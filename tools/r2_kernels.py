@@ -1,7 +1,7 @@
 """A few launches of each kernel of interest, for ncu captures and quick timings:
     python tools/r2_kernels.py <what> [reps]
 what: sweep (k_sweep_lin<checked>) | sweep_fast | point (k_stream_rx2<checked,inject>) | rx_fast | rx_exact (k_stream_rx2<.,none>)
-      | tx_fast | tx_exact (k_tx_frames2) | mc_fast | mc_exact (k_mc_philox) | mp_fast | mp_exact | all (timings of all of them)"""
+      | tx_fast | tx_exact (k_tx_frames2) | power | power_full | power_allref (k_frame_power_tiled) | mc_fast | mc_exact (k_mc_philox) | mp_fast | mp_exact | all (timings of all of them)"""
 import os
 import sys
 
@@ -66,6 +66,18 @@ def run(name):
         tx()
         ms = timed(lambda: o._check(lib.ofdm_rx_frames(h, frames.data_ptr(), bits.data_ptr(), n, 2, mode, cnt.data_ptr(), None)))
         return ms, "%.0f GB/s" % (n * 2072 / ms / 1e6)
+    if name in ("power", "power_full", "power_allref"):
+        # the exact power chain: of transmitter frames (LTS prefix skipped: 1280 B read per frame) as the sweep runs it (timed as
+        # transmitter + power minus transmitter alone), or of arbitrary frames (2560 B), or with every sample through hypot()
+        bits, g, frames, power = setup(N, pkg.MODE_EXACT)
+        if name == "power":
+            a = timed(lambda: o._check(lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), power.data_ptr(), N, 2, pkg.MODE_EXACT)))
+            b = timed(lambda: o._check(lib.ofdm_tx_frames(h, bits.data_ptr(), frames.data_ptr(), None, N, 2, pkg.MODE_EXACT)))
+            return a - b, "%.0f GB/s (transmitter alone %.4f ms)" % (N * 1284 / (a - b) / 1e6, b)
+        o.set_option("power_margin", 1 << 28 if name == "power_allref" else 16)
+        ms = timed(lambda: o._check(lib.ofdm_frame_power(h, frames.data_ptr(), power.data_ptr(), N, 320, pkg.MODE_EXACT)))
+        o.set_option("power_margin", 16)
+        return ms, "%.0f GB/s" % (N * 2564 / ms / 1e6)
     if name in ("mc_fast", "mc_exact", "mp_fast", "mp_exact"):
         cnt = o.new_counters(21)
         taps = 8 if name.startswith("mp") else 0
@@ -76,7 +88,7 @@ def run(name):
     raise SystemExit("unknown kernel " + name)
 
 
-names = ["sweep", "sweep_fast", "point", "point_fast", "rx_fast", "rx_exact", "tx_fast", "tx_exact", "mc_fast", "mc_exact", "mp_fast", "mp_exact"] if what == "all" else [what]
+names = ["power", "power_full", "power_allref", "sweep", "sweep_fast", "point", "point_fast", "rx_fast", "rx_exact", "tx_fast", "tx_exact", "mc_fast", "mc_exact", "mp_fast", "mp_exact"] if what == "all" else [what]
 for nm in names:
     ms, rate = run(nm)
     print("%-12s %8.4f ms  %s" % (nm, ms, rate), flush=True)
