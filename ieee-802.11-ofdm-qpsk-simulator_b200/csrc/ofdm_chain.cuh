@@ -127,7 +127,8 @@ constexpr float kEvmGuard = 512.f;
 // LEVEL 2: decisions and EVM guard verified (kArithChecked).  LEVEL 1: EVM guard only -- what the fast kernels of round 2 use
 // so that their EVM sums stay within 1e-5 of the reference's too (the rare frames with a tiny |H| bin are replayed exactly).
 // THR_GIVEN: the caller supplies the decision threshold (rF carries it; rH2 unused) -- the sweep kernel evaluates it as a
-// polynomial in sigma per item instead of from |F|_1 and |G|_1 per point (ofdm_sweep.cuh).
+// polynomial in sigma per item instead of from |F|_1 and |G|_1 per point (ofdm_sweep.cuh) -- and has bounded |G|^2 < 1.6e14
+// for the whole frame from the window norms.
 template <int LEVEL, bool THR_GIVEN = false>
 __device__ __forceinline__ uint32_t process_bin_spec(float2 F, float2 G, float k, uint32_t txp, float rF, float rH2, float den_min4,
                                                      float2 &e2, bool &doubt)
@@ -152,9 +153,10 @@ __device__ __forceinline__ uint32_t process_bin_spec(float2 F, float2 G, float k
             thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
         }
         // reference numerator >= 1e-30 in magnitude and reference |H|^2 < 1e14: the float quotient keeps its sign (>= 1e-44)
-        safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 2e-30f && den < 1.6e14f && den > den_min4;
+        // THR_GIVEN callers have checked den < 1.6e14 for all bins of the frame at once (from the window norms)
+        safe = (fminf(fabsf(sr), fabsf(si)) - thr) > 2e-30f && (THR_GIVEN || den < 1.6e14f) && den > den_min4;
     } else {
-        safe = den < 1.6e14f && den > den_min4;
+        safe = (THR_GIVEN || den < 1.6e14f) && den > den_min4;
     }
     doubt = doubt || !safe;
     // E - tx = (S * inv) * k - (+-1/sqrt(2)); e2 collects the squares of the two rails separately (summed per frame)

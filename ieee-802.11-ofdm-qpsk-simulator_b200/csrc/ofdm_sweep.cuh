@@ -50,6 +50,15 @@ struct alignas(16) SweepWarp {
 };
 static_assert(sizeof(SweepWarp) % 16 == 0 && offsetof(SweepWarp, st) % 16 == 0 && offsetof(SweepWarp, norm) % 16 == 0, "SweepWarp alignment");
 
+// |z| rounded up: approximate square root (2 ulps), rounding of the sum of squares, squares that underflow (below 1.1e-19
+// in modulus: the floor term)
+__device__ __forceinline__ float modulus_up(float2 z)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(z.x, z.x, z.y * z.y)));
+    return fmaf(r, 1.000004f, 2e-19f);
+}
+
 template <int ARITH>
 __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
 {
@@ -166,13 +175,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             FN[t] = (&ws.fn[2][0])[ic.f_off[t]];
             const bool sym0 = ic.f_off[t] < kWin;                              // the item's symbol
             const float rFX = sym0 ? rX.z : rX.w, rFN = sym0 ? rN.z : rN.w;
-            // The decision threshold of process_bin_spec, r_F (|G|_1 + r_H2) + r_H2 |F|_1 + 1.2e-7 |F|_1 |G|_1, as a polynomial in
-            // sigma: with |F|_1 <= |FX|_1 + sigma |FN|_1, |G|_1 <= |GX|_1 + sigma |GN|_1 (triangle inequality) and the radii
-            // r = rX + sigma rN, every factor is a non-negative affine function of sigma, so the products are bounded by
-            // c0 + c1 sigma + c2 sigma^2 -- three coefficients per item and frame, two multiply-adds per SNR point.
+            // The decision threshold, r_F (|G| + r_H2) + r_H2 |F| + 2u |F| |G| (the numerator F conj(G) moves by at most
+            // |dF||G| + |F||dG| + |dF||dG| in either rail, and its fp32 evaluation errs by at most 2u (|ac| + |bd|) <= 2u |F||G|:
+            // Cauchy-Schwarz, moduli instead of the 1-norms process_bin_spec uses per point), as a polynomial in sigma: with
+            // |F| <= |FX| + sigma |FN|, |G| <= |GX| + sigma |GN| (triangle inequality) and the radii r = rX + sigma rN, every
+            // factor is a non-negative affine function of sigma, so the products are bounded by c0 + c1 sigma + c2 sigma^2 --
+            // three coefficients per item and frame, two multiply-adds per SNR point.  The moduli are rounded up (approximate
+            // square root, squares that underflow: windows below 1e-15 in norm are never speculated, so 2e-19 covers them).
             if (LEVEL >= 2) {
-                const float faX = fabsf(FX[t].x) + fabsf(FX[t].y), faN = fabsf(FN[t].x) + fabsf(FN[t].y);
-                const float hcX = fabsf(GX[t].x) + fabsf(GX[t].y), hcN = fabsf(GN[t].x) + fabsf(GN[t].y);
+                const float faX = modulus_up(FX[t]), faN = modulus_up(FN[t]);
+                const float hcX = modulus_up(GX[t]), hcN = modulus_up(GN[t]);
                 const float A0 = hcX + rHX, A1 = hcN + rHN;
                 c0[t] = fmaf(rFX, A0, fmaf(rHX, faX, 1.2e-7f * (faX * hcX)));
                 c1[t] = fmaf(rFX, A1, fmaf(rFN, A0, fmaf(rHX, faN, fmaf(rHN, faX, 1.2e-7f * fmaf(faX, hcN, faN * hcX)))));
@@ -196,12 +208,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
         uint2 *res = reinterpret_cast<uint2 *>(&ws.fn[0][0]);
         // Two SNR points per iteration: six independent decision chains per lane instead of three (the kernel runs four warps per
         // scheduler, so instruction-level parallelism inside a warp is what covers the rcp / multiply-add latencies).
+        const float g2_limit = p.radius_scale * 1.58e6f;        // 8 rH2 / radius_scale (1 + 1e-4) < sqrt(1.6e14); infinite radius: never
         auto eval_point = [&](float sg, uint32_t &pk, float &e2, bool &doubt) {          // straight-line: no votes, no branches
             const float2 sg2 = make_float2(sg, sg);
             const float rH2 = fmaf(sg, rHN, rHX);
             const float gd = p.evm_guard * rH2, den_min4 = gd * gd;
             float2 e2v = make_float2(0.f, 0.f);
-            pk = 0; doubt = false;
+            // every bin of G = A + B is at most 8 (|x_A| + sigma |g_A| + |x_B| + sigma |g_B|) = 8 rH2 / radius_scale in modulus:
+            // |G|^2 < 1.6e14 (the reference's quotient cannot overflow, process_bin_spec) is checked once per point
+            pk = 0; doubt = !(rH2 < g2_limit);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 const float2 F = __ffma2_rn(sg2, FN[t], FX[t]);
@@ -215,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             bool replay = true;
             if (LEVEL >= 2) {
                 // The polynomial is an upper bound of the per-point threshold (triangle inequality): before paying for a replay,
-                // recheck the point with the threshold of its actual |F|_1, |G|_1 -- a third of the doubtful points pass.
+                // recheck the point with the threshold of its actual |F|, |G|.
                 const float4 qX = *reinterpret_cast<const float4 *>(ws.norm), qN = *reinterpret_cast<const float4 *>(ws.norm + 4);
                 const float2 sg2 = make_float2(sg, sg);
                 const float rH2 = fmaf(sg, rHN, rHX);
@@ -229,7 +244,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
                     const float2 G = __ffma2_rn(sg2, GN[t], GX[t]);
                     const bool sym0 = ic.f_off[t] < kWin;
                     const float rF = fmaf(sg, sym0 ? qN.z : qN.w, sym0 ? qX.z : qX.w);
-                    pk2 += process_bin_spec<LEVEL>(F, G, k4[t], txp[t], rF, rH2, den_min4, e2w, doubt2);
+                    const float fa = modulus_up(F), hc = modulus_up(G);
+                    const float thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
+                    pk2 += process_bin_spec<LEVEL, true>(F, G, k4[t], txp[t], thr, rH2, den_min4, e2w, doubt2);
                 }
                 replay = __any_sync(0xffffffffu, doubt2);
             }
