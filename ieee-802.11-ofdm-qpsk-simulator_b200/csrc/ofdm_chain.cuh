@@ -73,14 +73,23 @@ __device__ __forceinline__ uint32_t item_eval(float2 F, float2 Hh, float sc, uin
 //                  decisions is not provably the reference's.  Error counts are therefore exactly those of
 //                  kArithExact; the EVM sums differ by fp32 rounding (1e-5 contract), as they already do there.
 //
-// The bound.  Both transforms compute the same DFT of the same 64 floats x.  A radix-2 stage maps an error vector
-// with norm growth sqrt(2) and adds a local error of at most (eps_mul + u) |v_out|_2, u = 2^-24; |v_out|_2 after
-// stage s is 2^(s/2) |x|_2, so six stages give  |err|_2 <= 6 (eps_mul + u) 8 |x|_2.  Reference (OFDM.c:282-312:
-// double twiddle, product rounded to float, float add): eps_mul <= u(1 + 2^-26), i.e. <= 97 u |x|_2.  fp32 path
-// (dft8, float twiddles, FMA complex multiply, dft8): eps_mul <= 4u for a non-trivial factor, plus the separate
-// twiddle stage: <= (6*5 + 4) 8 u |x|_2 = 272 u |x|_2.  The channel estimate adds the rounding of A + B (:848):
-// <= 2u |A + B| <= 32 u max(|x_A|_2, |x_B|_2).  Every bin of a window is therefore within
-//      radius = kRadius * |x|_2,   kRadius = 512 u  (>= 97 + 272 + 32 = 401, the rest is margin for the
+// The bound.  Both transforms compute the same DFT of the same 64 floats x (u = 2^-24).  A radix-2 stage is sqrt(2) times a
+// unitary map: an error introduced after stage s, of norm e |v_s|_2 with |v_s|_2 = 2^(s/2) |x|_2, reaches the output with
+// norm 2^((6-s)/2) e |v_s|_2 = 8 e |x|_2, whatever the stage, and no bin errs by more than the norm of the error vector.
+//   Reference (OFDM.c:282-312): per stage the double product w*b rounded to float (<= u(1 + 2^-26) |b|), then a float
+//   add (<= u |v_out|): 6 * 2u * 8 |x|_2 <= 97 u |x|_2.
+//   fp32 path (fft64_fast = dft8, twiddles, transpose, dft8; ofdm_device.cuh), stage by stage:
+//     dft8: three stages of complex additions (u |v_out| each; the factors -i are swaps and sign changes, exact) and one
+//           diagonal step on two of the eight values, b * W8^(1,3) = fl(fl(x +- y) * fl(sqrt(1/2))): (1+u)^2 (1 + 0.29u),
+//           <= 2.3 u |b|                                                                        ->  5.3 u   (5.5 charged)
+//     twiddles: cmul = (fma(a.x, b.x, -fl(a.y b.y)), fma(a.x, b.y, fl(a.y b.x))): componentwise u(|a.x b.x| + 2|a.y b.y|),
+//           u(|a.x b.y| + 2|a.y b.x|), so <= sqrt(5) u |a||b| in modulus; the float twiddle is within u of the true one
+//                                                                                               ->  3.3 u
+//     total (5.5 + 3.3 + 5.5) * 8 u |x|_2 = 114.4, charged as 116 u |x|_2.
+//   (Round 1 charged every fp32 stage 5u: 272 u.  The per-stage count above is what the code does.)
+// The channel estimate adds the rounding of A + B (:848): <= 2u |A + B| <= 32 u max(|x_A|_2, |x_B|_2).  Every bin of a
+// window is therefore within
+//      radius = kRadius * |x|_2,   kRadius = 320 u  (>= 97 + 116 + 32 (+ 32, below) = 277, the rest is margin for the
 // second-order terms, the approximate square root and the rounding of the threshold itself)
 // of the reference's value, for F, and (radius_A + radius_B)/2 for H.  With F = F~ + dF, H = H~ + dH the numerator
 // of the equaliser (:1050) moves by at most |dF| |H|_1 + |dH| |F|_1 + |dF||dH|, and its fp32 evaluation errs by
@@ -91,10 +100,10 @@ __device__ __forceinline__ uint32_t item_eval(float2 F, float2 Hh, float sc, uin
 // the reference as fl32(x + fl32(sigma_d * g)) (:651).  Per sample the two differ by at most 2u |sigma g| + 2u |x'|
 // (rounding of sigma, of the product, of the two sums), so for a window |delta|_2 <= 2u |sigma g|_2 + 2u |x'|_2
 // <= 4u |x'|_2 + 2u |x|_2 with x the clean samples, and the transform maps it to at most 8 |delta|_2 in any bin:
-// 32 u |x'|_2, charged to kRadius (97 + 272 + 32 + 32 = 433 <= 512), plus 16 u |x|_2 <= 16 u sqrt(len * P), P the
+// 32 u |x'|_2, charged to kRadius (97 + 116 + 32 + 32 = 277 <= 320), plus 16 u |x|_2 <= 16 u sqrt(len * P), P the
 // frame's mean power of :637-643 -- the kChanRadius term (18 u, margin included), which does not depend on the window.
 enum { kArithFast = 0, kArithExact = 1, kArithChecked = 2 };
-constexpr float kRadius = 512.f * 5.9604645e-8f;
+constexpr float kRadius = 320.f * 5.9604645e-8f;
 constexpr float kChanRadius = 18.f * 5.9604645e-8f;
 
 // frames the speculating kernels replayed exactly are counted per context (a device word owned by the ofdm_ctx, passed in the
@@ -117,9 +126,10 @@ __device__ __forceinline__ float window_radius(float2 n2v, float scale, float ex
 // reference's.  rF / rH: error radii of F and H.  den_min: bins whose |H|^2 is below it are not trusted either --
 // not for the decisions but for the EVM sum, which at low SNR is dominated by the few bins with a tiny estimate
 // (|E|^2 ~ 1/|H|^2), where the fp32 transform's error in H would show: with |H| >= kEvmGuard radii the relative
-// error of an accepted quotient stays below ~1e-5 for the rarest accepted bins (the bound is about 300x the typical
-// error) and the sums agree with the all-exact kernel's to ~1e-7 (2048 radii: 1e-8, at 4x the replays on fading channels).
-constexpr float kEvmGuard = 512.f;
+// error of an accepted quotient stays below ~1e-5 for the rarest accepted bins (the bound is about 200x the typical
+// error) and the sums agree with the all-exact kernel's to ~1e-7 (4x the guard: 1e-8, at 4x the replays on fading channels).
+// 820 radii of 320 u = the 512 radii of 512 u of the first round-2 builds: the guard is about typical errors, not the bound.
+constexpr float kEvmGuard = 820.f;
 //
 // The estimate comes in unscaled, G = A + B with H = sc G, sc = +-0.5 (:848): powers of two commute with every rounding
 // here, so the test is done on G (numerator, thresholds and guards scaled accordingly, rH2 = 2 rH) and the quotient

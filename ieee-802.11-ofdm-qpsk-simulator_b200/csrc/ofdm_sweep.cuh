@@ -13,12 +13,12 @@
 // verified against a rigorous bound on |speculated - reference|, doubtful (frame, SNR point)s replayed in the
 // reference's arithmetic from global memory (stream_frame_replay).  The bound for this kernel, per bin of a window with
 // clean samples x, draws g and S = |x|_2 + sigma |g|_2 (u = 2^-24; |X_k| <= 8 |x|_2 by Cauchy-Schwarz):
-//   speculated  fl(X~ + sigma_f N~):  272 u |x|_2 + 272 u sigma |g|_2  (the two fp32 transforms, ofdm_chain.cuh)
+//   speculated  fl(X~ + sigma_f N~):  116 u |x|_2 + 116 u sigma |g|_2  (the two fp32 transforms, ofdm_chain.cuh)
 //                                     + 8 u sigma |g|_2  (sigma_f = fl32(sigma_d))  + 8 u S  (rounding of the multiply-add)
 //   reference   FFT_ref(x'), x' = fl(x + fl(sigma_d g)) (:651):  97 u |x'|_2 (its butterflies) + 8 (u sigma |g|_2 + u |x'|_2)
 //                                     (the two roundings of x'), |x'|_2 <= S (1 + u)
 //   channel estimate: + 32 u S for the reference's rounding of A + B, + 16 u S for fl(X~_A + X~_B), fl(N~_A + N~_B)
-//   => within (272 + 8 + 8 + 97 + 16 + 32 + 16) u S = 449 u S <= kRadius S = 512 u S.
+//   => within (116 + 8 + 8 + 97 + 16 + 32 + 16) u S = 293 u S <= kRadius S = 320 u S.
 // A window's radius is therefore  kRadius |x|_2 + sigma kRadius |g|_2:  two norms per window per frame, one multiply-add
 // per SNR point.  kArithFast keeps only the EVM guard (bins with a tiny channel estimate are replayed exactly).
 #pragma once

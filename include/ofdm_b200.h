@@ -102,7 +102,7 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *                            both give the same error counts)
  *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path)
  *   "general_stream"    = 1  two-symbol frames also take the multi-pass streaming kernel that serves every other frame shape
- *   "evm_guard"         = N  bins whose channel estimate is smaller than N error radii are replayed exactly (default 512): the
+ *   "evm_guard"         = N  bins whose channel estimate is smaller than N error radii are replayed exactly (default 820): the
  *                            EVM sums' distance from the all-exact kernel's against the number of replays
  *   "power_margin"      = N  the exact frame power speculates each term of the serial float sum as x^2 + y^2 and takes the
  *                            reference's hypot()^2 where the running sum is within N double ulps of a tie between two floats
