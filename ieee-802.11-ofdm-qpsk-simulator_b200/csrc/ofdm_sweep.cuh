@@ -192,13 +192,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             } else { c0[t] = c1[t] = c2[t] = 0.f; }
         }
         __syncwarp();                                         // everyone holds its items: fx / fn may be overwritten
-        uint32_t txp[3];
+        // Fold the transmitted rails' signs and the sign of sc into the items (exact: negations commute with every rounding).
+        // With S = F conj(G): negating F.x and G.y negates S.x alone, negating F.y and G.y negates S.y alone, so after
+        //   F.x ^= (tx I-rail sign ^ sign sc),  F.y ^= (tx Q-rail sign ^ sign sc),  G.y ^= (tx I-rail sign ^ tx Q-rail sign)
+        // every item looks as if (+1, +1)/sqrt(2) had been sent through sc = +1/2: a rail error is the sign bit of S, the error
+        // vector is 2 S / |G|^2 - (h, h), and |G|^2, the moduli and the thresholds are unchanged.  The replay reads global memory.
 #pragma unroll
-        for (int t = 0; t < 3; ++t) txp[t] = txw[t] >> ic.shift[t];
+        for (int t = 0; t < 3; ++t) {
+            const uint32_t tp = txw[t] >> ic.shift[t];
+            const uint32_t kb = __float_as_uint(k4[t]) & 0x80000000u;
+            const uint32_t fq = (tp << 31) ^ kb, fi = ((tp ^ (tp >> 1)) << 31) ^ kb, gq = (tp >> 1) << 31;
+            FX[t] = make_float2(__uint_as_float(__float_as_uint(FX[t].x) ^ fi), __uint_as_float(__float_as_uint(FX[t].y) ^ fq));
+            FN[t] = make_float2(__uint_as_float(__float_as_uint(FN[t].x) ^ fi), __uint_as_float(__float_as_uint(FN[t].y) ^ fq));
+            GX[t].y = __uint_as_float(__float_as_uint(GX[t].y) ^ gq);
+            GN[t].y = __uint_as_float(__float_as_uint(GN[t].y) ^ gq);
+        }
         // the noise scale of every SNR point, (float)sqrt((double)(P / snr)) (:647, :651), one (two) per lane
         float sig_lo = 0.f, sig_hi = 0.f;
         if (lane < p.n_snr) sig_lo = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane])));
         if (lane + 32 < p.n_snr) sig_hi = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane + 32])));
+        // ... through shared memory (a free noise tile): one broadcast 64-bit load per pair of points in the loop
+        float *sigs = reinterpret_cast<float *>(&ws.fn[1][0]);
+        sigs[lane] = sig_lo; sigs[lane + 32] = sig_hi;
+        if (lane < 2) sigs[64 + lane] = 0.f;
+        __syncwarp();
 
         // ---- SNR loop OFDM.c:1202: one packed multiply-add per value, then the decision stage.  Per-point results
         // {packed rail errors, sum |e|^2} go through 64 words of shared memory (the noise tiles are free by now and the
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
                 const float2 F = __ffma2_rn(sg2, FN[t], FX[t]);
                 const float2 G = __ffma2_rn(sg2, GN[t], GX[t]);
                 const float thr = fmaf(fmaf(c2[t], sg, c1[t]), sg, c0[t]);
-                pk += process_bin_spec<LEVEL, true>(F, G, k4[t], txp[t], thr, rH2, den_min4, e2v, doubt);
+                pk += process_bin_spec<LEVEL, true>(F, G, 2.f, 0u, thr, rH2, den_min4, e2v, doubt);
             }
             e2 = e2v.x + e2v.y;
         };
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
                     const float rF = fmaf(sg, sym0 ? qN.z : qN.w, sym0 ? qX.z : qX.w);
                     const float fa = modulus_up(F), hc = modulus_up(G);
                     const float thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
-                    pk2 += process_bin_spec<LEVEL, true>(F, G, k4[t], txp[t], thr, rH2, den_min4, e2w, doubt2);
+                    pk2 += process_bin_spec<LEVEL, true>(F, G, 2.f, 0u, thr, rH2, den_min4, e2w, doubt2);
                 }
                 replay = __any_sync(0xffffffffu, doubt2);
             }
@@ -276,8 +293,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             }
             const bool two = kStep == 2 && si + 1 < p.n_snr;                             // warp-uniform
             const int sj = two ? si + 1 : si;
-            const float sg0 = __shfl_sync(0xffffffffu, si < 32 ? sig_lo : sig_hi, si & 31);
-            const float sg1 = __shfl_sync(0xffffffffu, sj < 32 ? sig_lo : sig_hi, sj & 31);
+            float sg0, sg1;
+            if (kStep == 2) { const float2 sp = *reinterpret_cast<const float2 *>(sigs + si); sg0 = sp.x; sg1 = sp.y; }   // si even; 0 past the end
+            else { sg0 = sigs[si]; sg1 = 0.f; }
             uint32_t pk0, pk1;
             float e20, e21;
             bool d0, d1;
