@@ -208,9 +208,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             GN[t].y = __uint_as_float(__float_as_uint(GN[t].y) ^ gq);
         }
         // the noise scale of every SNR point, (float)sqrt((double)(P / snr)) (:647, :651), one (two) per lane
+        // (the double square root rounded to float is the correctly rounded float square root: 53 >= 2 * 24 + 2 bits, so the
+        // second rounding cannot change the result -- no double arithmetic needed here; the replay takes sigma in double)
         float sig_lo = 0.f, sig_hi = 0.f;
-        if (lane < p.n_snr) sig_lo = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane])));
-        if (lane + 32 < p.n_snr) sig_hi = __double2float_rn(__dsqrt_rn((double)__fdiv_rn(P, p.snr_lin[lane + 32])));
+        if (lane < p.n_snr) sig_lo = __fsqrt_rn(__fdiv_rn(P, p.snr_lin[lane]));
+        if (lane + 32 < p.n_snr) sig_hi = __fsqrt_rn(__fdiv_rn(P, p.snr_lin[lane + 32]));
         // ... through shared memory (a free noise tile): one broadcast 64-bit load per pair of points in the loop
         float *sigs = reinterpret_cast<float *>(&ws.fn[1][0]);
         sigs[lane] = sig_lo; sigs[lane + 32] = sig_hi;
@@ -226,22 +228,27 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
         // Two SNR points per iteration: six independent decision chains per lane instead of three (the kernel runs four warps per
         // scheduler, so instruction-level parallelism inside a warp is what covers the rcp / multiply-add latencies).
         const float g2_limit = p.radius_scale * 1.58e6f;        // 8 rH2 / radius_scale (1 + 1e-4) < sqrt(1.6e14); infinite radius: never
-        auto eval_point = [&](float sg, uint32_t &pk, float &e2, bool &doubt) {          // straight-line: no votes, no branches
-            const float2 sg2 = make_float2(sg, sg);
-            const float rH2 = fmaf(sg, rHN, rHX);
-            const float gd = p.evm_guard * rH2, den_min4 = gd * gd;
-            float2 e2v = make_float2(0.f, 0.f);
+        // one SNR point is prepared (noise scale, channel radius, guards) and then evaluated item by item, so that the loop body
+        // below can place the steps of the previous pair's warp reduction between the items
+        struct PointState { float sg, rH2, den_min4; float2 e2v; uint32_t pk; bool doubt; };
+        auto point_begin = [&](float sg) {
+            PointState q;
+            q.sg = sg;
+            q.rH2 = fmaf(sg, rHN, rHX);
+            const float gd = p.evm_guard * q.rH2;
+            q.den_min4 = gd * gd;
+            q.e2v = make_float2(0.f, 0.f);
             // every bin of G = A + B is at most 8 (|x_A| + sigma |g_A| + |x_B| + sigma |g_B|) = 8 rH2 / radius_scale in modulus:
             // |G|^2 < 1.6e14 (the reference's quotient cannot overflow, process_bin_spec) is checked once per point
-            pk = 0; doubt = !(rH2 < g2_limit);
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const float2 F = __ffma2_rn(sg2, FN[t], FX[t]);
-                const float2 G = __ffma2_rn(sg2, GN[t], GX[t]);
-                const float thr = fmaf(fmaf(c2[t], sg, c1[t]), sg, c0[t]);
-                pk += process_bin_spec<LEVEL, true>(F, G, 2.f, 0u, thr, rH2, den_min4, e2v, doubt);
-            }
-            e2 = e2v.x + e2v.y;
+            q.pk = 0; q.doubt = !(q.rH2 < g2_limit);
+            return q;
+        };
+        auto point_item = [&](PointState &q, int t) {                                    // straight-line: no votes, no branches
+            const float2 sg2 = make_float2(q.sg, q.sg);
+            const float2 F = __ffma2_rn(sg2, FN[t], FX[t]);
+            const float2 G = __ffma2_rn(sg2, GN[t], GX[t]);
+            const float thr = fmaf(fmaf(c2[t], q.sg, c1[t]), q.sg, c0[t]);
+            q.pk += process_bin_spec<LEVEL, true>(F, G, 2.f, 0u, thr, q.rH2, q.den_min4, q.e2v, q.doubt);
         };
         auto resolve_point = [&](int si, float sg, uint32_t &pk, float &e2) {             // rare: a doubtful point (whole warp calls)
             bool replay = true;
@@ -275,50 +282,68 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
             }
         };
         // The warp sums of a pair (one REDUX each for the packed counts, five dependent shuffle steps for the two sums |e|^2,
-        // packed) are finished one iteration late, on top of the next pair's straight-line arithmetic.
-        uint32_t pk_pend0 = 0, pk_pend1 = 0;
+        // packed) are finished one iteration late: the REDUXes are issued at the top, the shuffle steps sit between the items of
+        // the next pair (a warp issues in order: a step placed right after the previous one would wait out its ~30 cycles).
+        uint32_t pk_raw0 = 0, pk_raw1 = 0;                      // the previous pair's per-lane packed counts
         float2 e2_pend = make_float2(0.f, 0.f);
         // measured: the pair pays for the verified decisions (4.13 -> 3.97 ms); the guarded-EVM-only loop is faster one point at a time
         constexpr int kStep = LEVEL >= 2 ? 2 : 1;
+        float2 red = make_float2(0.f, 0.f), red_in = red;
+        // `after`: a sum of squares whose sign bit (never set) joins the shuffle's lane mask -- a data dependency that keeps the
+        // assembler from hoisting the whole shuffle chain to the top of the loop body.  Measured: spreading the steps pays in
+        // the one-point loop of the fast arithmetic (3.30 -> 3.19 ms) and costs in the two-point loop (3.79 -> 3.87 ms), where
+        // the hoisted chain leaves the scheduler more freedom for the six item chains.
+        constexpr bool kSpread = LEVEL < 2;
+        auto red_issue = [&](int o, float after) {
+            const int m = kSpread ? o | (int)(__float_as_uint(after) & 0x80000000u) : o;
+            red_in = make_float2(__shfl_xor_sync(0xffffffffu, red.x, m), __shfl_xor_sync(0xffffffffu, red.y, m));
+        };
+        auto red_take = [&]() { red = __fadd2_rn(red, red_in); };
         for (int si = 0; si < p.n_snr; si += kStep) {
-            {
-                float2 r = e2_pend;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    r = __fadd2_rn(r, make_float2(__shfl_xor_sync(0xffffffffu, r.x, o), __shfl_xor_sync(0xffffffffu, r.y, o)));
-                if (lane == 0 && si > 0) {
-                    res[si - kStep] = make_uint2(pk_pend0, __float_as_uint(r.x));
-                    if (kStep == 2) res[si - 1] = make_uint2(pk_pend1, __float_as_uint(r.y));
-                }
-            }
+            const uint32_t pk_sum0 = __reduce_add_sync(0xffffffffu, pk_raw0);            // one REDUX: the three 8-bit fields stay below 97
+            const uint32_t pk_sum1 = kStep == 2 ? __reduce_add_sync(0xffffffffu, pk_raw1) : 0u;
+            red = e2_pend;
+            red_issue(16, 0.f);
             const bool two = kStep == 2 && si + 1 < p.n_snr;                             // warp-uniform
             const int sj = two ? si + 1 : si;
             float sg0, sg1;
             if (kStep == 2) { const float2 sp = *reinterpret_cast<const float2 *>(sigs + si); sg0 = sp.x; sg1 = sp.y; }   // si even; 0 past the end
             else { sg0 = sigs[si]; sg1 = 0.f; }
-            uint32_t pk0, pk1;
-            float e20, e21;
-            bool d0, d1;
-            eval_point(sg0, pk0, e20, d0);
-            if (kStep == 2) eval_point(sg1, pk1, e21, d1);
-            else { pk1 = 0; e21 = 0.f; d1 = false; }
-            if (__any_sync(0xffffffffu, d0 || d1)) {
-                if (__any_sync(0xffffffffu, d0)) resolve_point(si, sg0, pk0, e20);
-                if (two && __any_sync(0xffffffffu, d1)) resolve_point(sj, sg1, pk1, e21);
+            PointState q0 = point_begin(sg0), q1 = point_begin(sg1);
+            point_item(q0, 0); red_take(); red_issue(8, q0.e2v.x);
+            point_item(q0, 1); red_take(); red_issue(4, q0.e2v.x);
+            point_item(q0, 2); red_take(); red_issue(2, q0.e2v.x);
+            if (kStep == 2) {
+                point_item(q1, 0); red_take(); red_issue(1, q1.e2v.x);
+                point_item(q1, 1); red_take();
+            } else {
+                red_take(); red_issue(1, 0.f); red_take();
             }
-            pk_pend0 = __reduce_add_sync(0xffffffffu, pk0);         // one REDUX: the three 8-bit fields stay below 97
-            pk_pend1 = __reduce_add_sync(0xffffffffu, pk1);
+            if (lane == 0 && si > 0) {
+                res[si - kStep] = make_uint2(pk_sum0, __float_as_uint(red.x));
+                if (kStep == 2) res[si - 1] = make_uint2(pk_sum1, __float_as_uint(red.y));
+            }
+            if (kStep == 2) point_item(q1, 2);
+            uint32_t pk0 = q0.pk, pk1 = q1.pk;
+            float e20 = q0.e2v.x + q0.e2v.y, e21 = q1.e2v.x + q1.e2v.y;
+            if (__any_sync(0xffffffffu, q0.doubt || (kStep == 2 && q1.doubt))) {
+                if (__any_sync(0xffffffffu, q0.doubt)) resolve_point(si, sg0, pk0, e20);
+                if (two && __any_sync(0xffffffffu, q1.doubt)) resolve_point(sj, sg1, pk1, e21);
+            }
+            pk_raw0 = pk0; pk_raw1 = pk1;
             e2_pend = make_float2(e20, e21);
         }
         {
+            const uint32_t pk_sum0 = __reduce_add_sync(0xffffffffu, pk_raw0);
+            const uint32_t pk_sum1 = kStep == 2 ? __reduce_add_sync(0xffffffffu, pk_raw1) : 0u;
             float2 r = e2_pend;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
                 r = __fadd2_rn(r, make_float2(__shfl_xor_sync(0xffffffffu, r.x, o), __shfl_xor_sync(0xffffffffu, r.y, o)));
             const int last = (p.n_snr - 1) & ~(kStep - 1);                               // first point of the last group
             if (lane == 0) {
-                res[last] = make_uint2(pk_pend0, __float_as_uint(r.x));
-                if (last + 1 < p.n_snr) res[last + 1] = make_uint2(pk_pend1, __float_as_uint(r.y));
+                res[last] = make_uint2(pk_sum0, __float_as_uint(r.x));
+                if (last + 1 < p.n_snr) res[last + 1] = make_uint2(pk_sum1, __float_as_uint(r.y));
             }
         }
         __syncwarp();
