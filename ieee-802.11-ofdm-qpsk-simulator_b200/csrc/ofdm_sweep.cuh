@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
         // second rounding cannot change the result -- no double arithmetic needed here; the replay takes sigma in double)
         float sig_lo = 0.f, sig_hi = 0.f;
         if (lane < p.n_snr) sig_lo = __fsqrt_rn(__fdiv_rn(P, p.snr_lin[lane]));
-        if (lane + 32 < p.n_snr) sig_hi = __fsqrt_rn(__fdiv_rn(P, p.snr_lin[lane + 32]));
+        if (p.n_snr > 32 && lane + 32 < p.n_snr) sig_hi = __fsqrt_rn(__fdiv_rn(P, p.snr_lin[lane + 32]));
         // ... through shared memory (a free noise tile): one broadcast 64-bit load per pair of points in the loop
         float *sigs = reinterpret_cast<float *>(&ws.fn[1][0]);
         sigs[lane] = sig_lo; sigs[lane + 32] = sig_hi;
@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_sweep_lin(SweepParams p)
         // the lane that owns an SNR point books the frame's result for it (lanes beyond n_snr read stale words and add nothing)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            if (h == 1 && p.n_snr <= 32) break;                                         // warp-uniform: no second half to book
             const uint2 r = res[lane + 32 * h];
             const bool mine = lane + 32 * h < p.n_snr;
             const uint32_t pk = mine ? r.x : 0u;
