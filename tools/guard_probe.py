@@ -18,7 +18,7 @@ g = torch.randn((n, 320), dtype=torch.float32, device=o.device, generator=gen)
 o.set_option("exact_speculation", 0)
 ref = o.sweep_inject_dev(bits, g, n, 2, snr, pkg.MODE_EXACT)
 o.set_option("exact_speculation", 1)
-for guard in (512, 256, 128, 64, 32, 8):
+for guard in (3280, 820, 410, 205, 102, 51, 13):
     o.set_option("evm_guard", guard)
     for fused in (1, 0):
         o.set_option("fused_sweep", fused)
