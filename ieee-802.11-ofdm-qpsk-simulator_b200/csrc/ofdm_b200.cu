@@ -10,6 +10,7 @@
 #include <utility>
 
 #include "ofdm_chain.cuh"
+#include "ofdm_stream.cuh"
 #include "ofdm_sweep.cuh"
 
 using namespace ofdm;
@@ -26,6 +27,8 @@ struct ofdm_ctx {
     bool checked = true;             // EXACT sweeps speculate in fp32, verify, and replay exactly (kArithChecked)
     bool force_replay = false;       // testing knob: the verification fails every frame
     bool general_stream = false;     // testing knob: two-symbol frames through the multi-pass streaming kernel too
+    int stream_warps = 6;            // k_stream_quad: warps per block (6: 168 registers, 12 warps per SM; 8: 128 registers, 16 warps per SM)
+    int stream_layout = 0;           // streaming receivers: 0 = one frame per lane group (k_stream_quad), 1 = one frame per warp (k_stream_rx2 / rxn)
     bool fused_sweep = true;         // ofdm_sweep_inject_*: the all-SNR kernel k_sweep_lin (default frame shape) instead of one launch per SNR point
     float evm_guard = kEvmGuard;     // tuning knob: bins with |H| below this many error radii are replayed exactly (EVM accuracy vs replays)
     uint32_t power_margin = 16;      // k_frame_power_tiled: samples whose running sum is within this many double ulps of a float tie take the reference's operations
@@ -228,6 +231,24 @@ int launch_stream_n(ofdm_ctx *ctx, const RxParams &p)
     k<<<grid, kThreads, smem, ctx->stream>>>(p);
     return check_launch(ctx, "k_stream_rxn");
 }
+template <int ARITH, int NOISE, int WARPS>
+int launch_stream_quad_w(ofdm_ctx *ctx, const RxParams &p)
+{
+    auto k = k_stream_quad<ARITH, NOISE, WARPS>;
+    const size_t smem = quad_smem_bytes<NOISE>(WARPS);
+    OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long full = (long)per_sm * ctx->sm_count, need = (p.n_frames + WARPS * 4 - 1) / (WARPS * 4);      // a warp works on four frames at a time
+    const long grid = need < full ? need : full;
+    k<<<(int)(grid < 1 ? 1 : grid), WARPS * 32, smem, ctx->stream>>>(p);
+    return check_launch(ctx, "k_stream_quad");
+}
+template <int ARITH, int NOISE>
+int launch_stream_quad(ofdm_ctx *ctx, const RxParams &p)
+{
+    return ctx->stream_warps == 8 ? launch_stream_quad_w<ARITH, NOISE, 8>(ctx, p) : launch_stream_quad_w<ARITH, NOISE, 6>(ctx, p);
+}
 // error radii of the speculating EXACT kernels (ofdm_chain.cuh: kRadius, kChanRadius)
 void set_radius(ofdm_ctx *ctx, RxParams &q)
 {
@@ -254,7 +275,22 @@ int launch_rx_any(ofdm_ctx *ctx, int mode, int noise, const RxParams &p)
     const bool dump = d.H || d.eq || d.sliced || d.bits || d.frame_bit_errors || d.frame_evm_lin;
     // default frame shape without per-bin outputs: the TMA-staged streaming kernel (bulk copies need 16-byte alignment)
     const bool aligned = ((uintptr_t)p.in % 16 == 0) && (noise != kNoiseInject || (uintptr_t)p.g % 16 == 0);
-    // other frame shapes (or "general_stream" = 1): the multi-pass streaming kernel
+    // speculating arithmetic, any frame shape: one frame per lane group (ofdm_stream.cuh)
+    if (!dump && aligned && !ctx->force_generic && ctx->stream_layout == 0 && (mode != OFDM_MODE_EXACT || ctx->checked)) {
+        RxParams q = p;
+        set_radius(ctx, q);             // exact mode verifies every decision; fast mode keeps the EVM guard (tiny |H| bins are replayed exactly)
+        if (mode == OFDM_MODE_EXACT) {
+            if (noise == kNoiseNone) return launch_stream_quad<kArithChecked, kNoiseNone>(ctx, q);
+            if (noise == kNoiseInject) return launch_stream_quad<kArithChecked, kNoiseInject>(ctx, q);
+            return launch_stream_quad<kArithChecked, kNoisePhilox>(ctx, q);
+        }
+        if (noise == kNoiseNone) return launch_stream_quad<kArithFast, kNoiseNone>(ctx, q);
+        if (noise == kNoiseInject) return launch_stream_quad<kArithFast, kNoiseInject>(ctx, q);
+        q.evm_guard = 0.f;              // Philox noise: statistical results, plain fp32 like the fused Monte-Carlo kernel
+        return launch_stream_quad<kArithFast, kNoisePhilox>(ctx, q);
+    }
+    // one frame per warp ("stream_layout" = 1, and the all-exact arithmetic): other frame shapes (or "general_stream" = 1) take
+    // the multi-pass streaming kernel
     if (!dump && aligned && !ctx->force_generic && (p.n_sym != 2 || ctx->general_stream)) {
         if (noise == kNoiseNone) return launch_stream_n_mode<kNoiseNone>(ctx, mode, p);
         if (noise == kNoiseInject) return launch_stream_n_mode<kNoiseInject>(ctx, mode, p);
@@ -479,6 +515,8 @@ int ofdm_ctx_set_option(ofdm_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "power_margin")) { if (value < 16 || value > (1 << 28)) return fail(ctx, OFDM_ERR_INVALID, "power_margin: 16..2^28 ulps"); ctx->power_margin = (uint32_t)value; return OFDM_OK; }
     if (!strcmp(name, "fused_sweep")) { ctx->fused_sweep = value != 0; return OFDM_OK; }
     if (!strcmp(name, "general_stream")) { ctx->general_stream = value != 0; return OFDM_OK; }
+    if (!strcmp(name, "stream_warps")) { if (value != 6 && value != 8) return fail(ctx, OFDM_ERR_INVALID, "stream_warps: 6 or 8"); ctx->stream_warps = value; return OFDM_OK; }
+    if (!strcmp(name, "stream_layout")) { if (value < 0 || value > 1) return fail(ctx, OFDM_ERR_INVALID, "stream_layout: 0..1"); ctx->stream_layout = value; return OFDM_OK; }
     if (!strcmp(name, "multipath_path")) { if (value < 0 || value > 2) return fail(ctx, OFDM_ERR_INVALID, "multipath_path: 0..2"); ctx->multipath_path = value; return OFDM_OK; }
     return fail(ctx, OFDM_ERR_INVALID, "unknown option");
 }

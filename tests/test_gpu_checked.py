@@ -52,9 +52,10 @@ def test_counts_match_oracle_and_all_exact(knobs, pkg, port, snr):
         assert abs(c.sum_err2 - acc.sum_err2) <= 1e-5 * acc.sum_err2, name
     assert res["replay_all"][1] == n_frames and res["all_exact"][1] == 0 and res["generic"][1] == 0
     assert res["checked"][1] <= n_frames // 10            # speculation must pay: few replays even at 0 dB
-    # the replay runs the all-exact kernel's arithmetic: same EVM sums up to the order of the double additions
+    # the replay runs the all-exact kernel's arithmetic bin by bin: same EVM sums up to the order in which the per-bin
+    # float terms of a frame and the per-frame terms of a lane are added up (one frame per lane group vs one per warp)
     a, b = res["replay_all"][0], res["all_exact"][0]
-    assert abs(a.sum_err2 - b.sum_err2) <= 1e-12 * b.sum_err2 and abs(a.sum_evm_lin - b.sum_evm_lin) <= 1e-12 * b.sum_evm_lin
+    assert abs(a.sum_err2 - b.sum_err2) <= 1e-6 * b.sum_err2 and abs(a.sum_evm_lin - b.sum_evm_lin) <= 1e-6 * b.sum_evm_lin
 
 
 def test_large_batch_low_snr(knobs, pkg):

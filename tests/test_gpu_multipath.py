@@ -83,7 +83,7 @@ def test_c_driver_multipath_sweep(tmp_path):
 @pytest.mark.parametrize("n_taps", [1, 5, 8, 16])
 def test_fused_multipath_sweep_equals_staged(ofdm, pkg, n_taps):
     """configs[4] on chip (k_mc_philox<., multipath>) against the staged path (TX, k_multipath, frame power, per-SNR receiver
-    kernels over HBM): the same taps, draws and arithmetic -> identical integer totals in both modes, EVM sums to rounding"""
+    kernels over HBM): the same taps and draws -> identical integer totals in EXACT mode, fp32 agreement in FAST mode"""
     snr = [0.0, 6.0, 12.0, 18.0]
     n = 40_000
     try:
@@ -95,12 +95,24 @@ def test_fused_multipath_sweep_equals_staged(ofdm, pkg, n_taps):
             ofdm.set_option("force_generic_rx", 1)                      # ... and through the generic receiver kernel
             generic = ofdm.mc_sweep_multipath(21, 700, n, 2, n_taps, snr, mode)
             ofdm.set_option("force_generic_rx", 0)
-            for a, b in zip(generic, staged):
-                assert (a.bit_errors, a.frames_in_error, a.rail_errors) == (b.bit_errors, b.frames_in_error, b.rail_errors), (n_taps, mode)
-            for a, b in zip(fused, staged):
-                assert (a.bit_errors, a.bits, a.frames_in_error, a.rail_errors, a.frames) == \
-                       (b.bit_errors, b.bits, b.frames_in_error, b.rail_errors, b.frames), (n_taps, mode)
-                assert abs(a.sum_err2 - b.sum_err2) <= 1e-5 * b.sum_err2, (n_taps, mode)
+            if mode == pkg.MODE_EXACT:
+                for a, b in zip(generic, staged):
+                    assert (a.bit_errors, a.frames_in_error, a.rail_errors) == (b.bit_errors, b.frames_in_error, b.rail_errors), (n_taps, mode)
+                for a, b in zip(fused, staged):
+                    assert (a.bit_errors, a.bits, a.frames_in_error, a.rail_errors, a.frames) == \
+                           (b.bit_errors, b.bits, b.frames_in_error, b.rail_errors, b.frames), (n_taps, mode)
+                    assert abs(a.sum_err2 - b.sum_err2) <= 1e-5 * b.sum_err2, (n_taps, mode)
+            else:
+                # FAST mode: plain fp32 with Philox noise (no EVM guard, statistical results).  The staged route's streaming
+                # receiver transforms the sum of the LTS halves once, the fused and the generic kernels each half: rails within
+                # fp32 rounding of the slicer boundary may fall either way, and the EVM sum -- dominated by the deepest fades,
+                # |e|^2 ~ 1/|H|^2 -- agrees to fp32 accuracy of those few bins, not to 1e-5
+                for other in (generic, fused):
+                    for a, b in zip(other, staged):
+                        assert (a.bits, a.frames) == (b.bits, b.frames)
+                        assert abs(a.bit_errors - b.bit_errors) <= 2 + 1e-5 * b.bit_errors and abs(a.rail_errors - b.rail_errors) <= 2 + 1e-5 * b.rail_errors
+                        assert abs(a.frames_in_error - b.frames_in_error) <= 2
+                        assert abs(a.sum_err2 - b.sum_err2) <= 5e-4 * b.sum_err2, (n_taps, mode)
     finally:
         ofdm.set_option("force_generic_rx", 0)
         ofdm.set_option("multipath_path", 0)

@@ -14,6 +14,10 @@ import __graft_entry__ as e
 pkg = e.load_pkg()
 o = pkg.Ofdm(0)
 dev, lib, h = o.device, o.lib, o.h
+if os.environ.get("STREAM_LAYOUT"):          # 0 = one frame per lane group (k_stream_quad), 1 = one frame per warp (k_stream_rx2)
+    o.set_option("stream_layout", int(os.environ["STREAM_LAYOUT"]))
+if os.environ.get("STREAM_WARPS"):           # k_stream_quad: 6 (168 registers, 12 warps per SM) or 8 (128 registers, 16 warps per SM) warps per block
+    o.set_option("stream_warps", int(os.environ["STREAM_WARPS"]))
 what = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 SNRS = [float(s) for s in range(21)]
