@@ -95,9 +95,15 @@ __device__ __forceinline__ float xor_sign(float x, uint32_t bits)
 {
     return __uint_as_float(__float_as_uint(x) ^ (bits & 0x80000000u));
 }
+// thr_a, thr_b (kArithChecked): the parts of the decision threshold that do not depend on the symbol, per frame and slot --
+// |speculated - reference numerator| <= rF |G|_1 + rH2 |F|_1 + rF rH2, + 2^-23 |F|_1 |G|_1 for the fp32 evaluation, i.e.
+// thr = rF thr_a + |F|_1 thr_b with thr_a = |G|_1 + rH2, thr_b = rH2 + 1.2e-7 |G|_1.
+// The verdict of a slot joins acc_s the same way: the sign bit of thr - min(|Re S|, |Im S|) is set exactly when the smaller
+// rail exceeds the threshold (an infinite or NaN threshold -- window energies out of range, non-finite samples -- gives +Inf
+// or the canonical NaN 0x7fffffff PTX arithmetic returns: sign bit clear, not trusted).
 template <int LEVEL>
-__device__ __forceinline__ void quad_slot(float2 F, float2 G, float inv2, uint32_t tb, bool valid, float rF, float rH2,
-                                          uint32_t &acc_i, uint32_t &acc_q, float2 &e2, bool &doubt)
+__device__ __forceinline__ void quad_slot(float2 F, float2 G, float inv2, uint32_t tb, bool valid, float rF, float thr_a, float thr_b,
+                                          uint32_t &acc_i, uint32_t &acc_q, uint32_t &acc_s, float2 &e2)
 {
     const uint32_t ta = tb << 1;
     const float2 pt = __fmul2_rn(make_float2(G.y, G.y), make_float2(F.y, F.x));
@@ -105,11 +111,11 @@ __device__ __forceinline__ void quad_slot(float2 F, float2 G, float inv2, uint32
     S.x = xor_sign(S.x, ta ^ tb);
     S.y = xor_sign(S.y, ta);
     if (LEVEL >= 2) {
-        // |speculated - reference numerator| <= rF |G|_1 + rH2 |F|_1 + rF rH2, + 2^-23 |F|_1 |G|_1 for the fp32 evaluation
-        const float fa = fabsf(F.x) + fabsf(F.y), hc = fabsf(G.x) + fabsf(G.y);
-        const float thr = fmaf(rF, hc + rH2, fmaf(rH2, fa, 1.2e-7f * (fa * hc)));
-        const bool safe = (fminf(fabsf(S.x), fabsf(S.y)) - thr) > 2e-30f;
-        doubt = doubt || (valid && !safe);
+        // trusted only if the smaller rail of the numerator exceeds the threshold by 2e-30 (the reference's float quotient then
+        // keeps its sign); NaN / Inf fail the comparison
+        const float fa = fabsf(F.x) + fabsf(F.y);
+        const float thr = fmaf(fa, thr_b, fmaf(rF, thr_a, 2e-30f));
+        acc_s = __funnelshift_l(__float_as_uint(thr - fminf(fabsf(S.x), fabsf(S.y))), acc_s, 1);
     }
     const float2 D = __ffma2_rn(S, make_float2(inv2, inv2), make_float2(-kQpsk, -kQpsk));
     if (valid) e2 = __ffma2_rn(D, D, e2);
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
             uint32_t nw0 = __ldg(wb), nw1 = __ldg(wb + 1), nw2 = __ldg(wb + 2);
             // ---- Channel_Estimation :830-850: the two halves added in time, one transform; G = A + B (unscaled) at bins u + 8j
             float2 G[8];
-            float inv2[7];
+            float inv2[7], thr_a[7], thr_b[7];
             float rH2;
             bool doubt = false;
             {
@@ -274,6 +280,10 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
                     const bool safe = den < 1.6e14f && den > den_min4;
                     doubt = doubt || (((ql.valid >> t) & 1u) && !safe);
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv2[t]) : "f"(0.5f * den));
+                    if (LEVEL >= 2) {
+                        const float hc = fabsf(Gt.x) + fabsf(Gt.y);
+                        thr_a[t] = hc + rH2; thr_b[t] = fmaf(1.2e-7f, hc, rH2);
+                    }
                 }
             }
             uint32_t f_i = 0, f_q = 0, f_both = 0;
@@ -293,15 +303,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
                 const uint32_t word_a = u < 2 ? w1 : w2;          // slot 1: bins 8 + u
                 const uint32_t word_b = u < 3 ? w2 : w0;          // slot 3: bins 24 + u (u < 3) / 32 + u (u > 5)
                 const uint32_t word_c = u == 7 ? w1 : w0;         // slot 5: bins 48 + u
-                uint32_t acc_i = 0, acc_q = 0;
+                uint32_t acc_i = 0, acc_q = 0, acc_s = 0;
 #pragma unroll
                 for (int t = 0; t < 7; ++t) {
                     const float2 F = t < 3 ? v[t] : (t == 3 ? (u < 3 ? v[3] : v[4]) : v[t + 1]);
                     const float2 Gt = t < 4 ? G[t] : G[t + 1];
                     const uint32_t w = t == 0 ? w1 : t == 1 ? word_a : t == 2 ? w2 : t == 3 ? word_b : t == 4 ? w0 : t == 5 ? word_c : w1;
                     const uint32_t tb = __funnelshift_l(0u, w, (t < 4 ? ql.sh_lo : ql.sh_hi) >> (5 * (t & 3)));      // w << (field & 31)
-                    quad_slot<LEVEL>(F, Gt, inv2[t], tb, (ql.valid >> t) & 1u, rF, rH2, acc_i, acc_q, e2v, doubt);
+                    quad_slot<LEVEL>(F, Gt, inv2[t], tb, (ql.valid >> t) & 1u, rF, thr_a[t], thr_b[t], acc_i, acc_q, acc_s, e2v);
                 }
+                if (LEVEL >= 2) doubt = doubt || (acc_s & ql.valid_rev) != ql.valid_rev;       // every data bin's decision must be trusted
                 acc_i &= ql.valid_rev; acc_q &= ql.valid_rev;
                 f_i += __popc(acc_i); f_q += __popc(acc_q); f_both += __popc(acc_i & acc_q);
             }
