@@ -12,11 +12,11 @@ RX at one SNR point: symbols/step = frames x n_sym x n_snr.
           and every SNR point costs a multiply-add per bin plus the verified decision stage).
   e2e     the same sweep through ofdm_sweep_inject_host: HOST (pinned) bits + draws, H2D copies,
           kernels and the D2H of the counters inside the timed region
-  roofline  the HBM-bound kernel of the path: k_stream_rx2<checked,inject>, the fused channel + receiver of ONE SNR
-            point (what the stage API ofdm_awgn_rx_inject launches, and what the sweep launched 21 times before
-            k_sweep_lin existed): algorithmic bytes (3100 B per frame) / mean launch time, CUDA events
-            around each launch of a dedicated loop of steps x 21 launches in this run.  sweep_kernel describes
-            k_sweep_lin, which is bound by instruction issue, not by HBM.
+  roofline  the HBM-bound kernel of the path: k_stream_quad<checked,inject>, the fused channel + receiver of ONE SNR
+            point, one frame per 8-lane group (what the stage API ofdm_awgn_rx_inject launches, and what the sweep
+            launched 21 times before k_sweep_lin existed): algorithmic bytes (3100 B per frame) / mean launch
+            time, CUDA events around each launch of a dedicated loop of steps x 21 launches in this run.  sweep_kernel
+            describes k_sweep_lin, which is bound by instruction issue, not by HBM.
   configs   configs[2] (streaming TX / RX of 16 Mi HBM-resident symbols, HBM GB/s fraction), configs[3] (fused on-chip
             Philox Monte-Carlo, fixed frame count and the until-100-errors-or-1e-7-budget rule), configs[4] (8-tap
             multipath): per-config throughput and roofline; at N > 1 configs[3] / [4] are sharded by global frame index
@@ -354,9 +354,9 @@ def bind_near_gpu(local):
 
 
 def kernel_metrics():
-    """ncu-derived pipe / issue utilisation of the kernels that are not HBM-bound (profiles/r2_kernel_metrics.json, written by
+    """ncu-derived pipe / issue utilisation of the kernels that are not HBM-bound (profiles/r2b_kernel_metrics.json, written by
     tools/ncu_summary.py from the committed ncu captures); None when the file is absent"""
-    path = os.path.join(ROOT, "profiles", "r2_kernel_metrics.json")
+    path = os.path.join(ROOT, "profiles", "r2b_kernel_metrics.json")
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f)
@@ -398,10 +398,13 @@ def run_configs(o, pkg, torch, dist, dev, args, rank, world):
         cnt.zero_()
         ms_rx = timed(lambda: o._check(lib.ofdm_rx_frames(h, frames.data_ptr(), bits.data_ptr(), n, N_SYM, mode, cnt.data_ptr(), None)), 5)
         assert int(o.read_counters(cnt)[0].bit_errors) == 0            # noise-free round trip
-        c2[name] = {"tx": {"ms": ms_tx, "roofline": {"bound": "hbm", "achieved": tx_bytes / ms_tx / 1e6, "peak": peak, "unit": "GB/s",
-                                                      "frac": tx_bytes / ms_tx / 1e6 / peak}},
-                    "rx": {"ms": ms_rx, "roofline": {"bound": "hbm", "achieved": rx_bytes / ms_rx / 1e6, "peak": peak, "unit": "GB/s",
-                                                      "frac": rx_bytes / ms_rx / 1e6 / peak}},
+        rx_kernel = "k_stream_quad<%s,none>" % ("fast" if name == "fast" else "checked")
+        c2[name] = {"tx": {"ms": ms_tx, "roofline": {"bound": "hbm", "kernel": "k_tx_frames2<%s>" % name, "achieved": tx_bytes / ms_tx / 1e6, "peak": peak,
+                                                      "unit": "GB/s", "frac": tx_bytes / ms_tx / 1e6 / peak}},
+                    "rx": {"ms": ms_rx, "roofline": dict({"bound": "hbm", "kernel": rx_kernel, "achieved": rx_bytes / ms_rx / 1e6, "peak": peak,
+                                                           "unit": "GB/s", "frac": rx_bytes / ms_rx / 1e6 / peak},
+                                                          **{k: v for k, v in km.get("k_stream_quad_%s_none" % ("fast" if name == "fast" else "checked"), {}).items()
+                                                             if k in ("warp_instructions_per_unit", "smem_wavefronts_per_unit", "issue_active_pct", "ipc", "registers", "source")})},
                     "symbols_per_s_tx_plus_rx": world * n * N_SYM / ((ms_tx + ms_rx) * 1e-3)}
     out["cfg2_streaming"] = c2
     del frames, bits
@@ -597,7 +600,7 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("k_stream_rx2_checked_inject_bytes_per_launch")
+                traffic = json.load(f).get("k_stream_quad_checked_inject_bytes_per_launch")
                 if traffic is not None and n_frames != 1_000_000:
                     traffic = traffic * n_frames / 1_000_000        # captured on the 1 M-frame launch
         ber = [c.bit_errors / max(1, c.bits) for c in resident_counts]
@@ -616,7 +619,7 @@ def run_gpu(args):
                         "host_buffer_bytes": int(n_frames * N_SYM * 12 + n_frames * flen * 4),
                         "d2h_bytes_per_step": int(n_snr * pkg.COUNTERS_BYTES)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_stream_rx2<checked,inject>", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "k_stream_quad<checked,inject>", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "kernel_ms_burst": float(np.mean(kernel_ms_burst)),
                              "frac_burst": BYTES_PER_FRAME_PASS * n_frames / (float(np.mean(kernel_ms_burst)) * 1e-3) / 1e9 / peak,

@@ -41,7 +41,13 @@ template <bool WITH_DRAWS> struct alignas(16) QuadSlot {        // bulk-copy des
 };
 template <> struct alignas(16) QuadSlot<false> { float2 x[4][kWin]; };
 
-template <int NOISE> __host__ __device__ constexpr int quad_depth() { return NOISE == kNoiseInject ? 3 : 4; }
+#ifndef OFDM_QUAD_DEPTH
+#define OFDM_QUAD_DEPTH 4               // A/B knobs (tools/ab.sh): ring slots per warp without / with injected draws
+#endif
+#ifndef OFDM_QUAD_DEPTH_DRAWS
+#define OFDM_QUAD_DEPTH_DRAWS 3
+#endif
+template <int NOISE> __host__ __device__ constexpr int quad_depth() { return NOISE == kNoiseInject ? OFDM_QUAD_DEPTH_DRAWS : OFDM_QUAD_DEPTH; }
 
 template <int NOISE> struct alignas(16) QuadWarp {
     float2 tile[kWarpTile];         // transform transpose tiles (one per lane group); scratch of the exact replay

@@ -10,10 +10,10 @@ N, NS, N2 = 1_000_000, 21, 8_388_608
 KERNELS = {   # what -> (key, units per launch, unit name, committed summary)
     "sweep": ("k_sweep_lin_checked", N * NS, "frame x SNR point"),
     "sweep_fast": ("k_sweep_lin_fast", N * NS, "frame x SNR point"),
-    "point": ("k_stream_rx2_checked_inject", N, "frame"),
-    "point_fast": ("k_stream_rx2_fast_inject", N, "frame"),
-    "rx_fast": ("k_stream_rx2_fast_none", N2, "frame"),
-    "rx_exact": ("k_stream_rx2_checked_none", N2, "frame"),
+    "point": ("k_stream_quad_checked_inject", N, "frame"),
+    "point_fast": ("k_stream_quad_fast_inject", N, "frame"),
+    "rx_fast": ("k_stream_quad_fast_none", N2, "frame"),
+    "rx_exact": ("k_stream_quad_checked_none", N2, "frame"),
     "tx_fast": ("k_tx_frames2_fast", N2, "frame"),
     "tx_exact": ("k_tx_frames2_exact", N2, "frame"),
     "mc_fast": ("k_mc_philox_fast", N * NS, "frame x SNR point"),
@@ -44,7 +44,7 @@ for what, (key, units, unit) in KERNELS.items():
         "smem_wavefronts_per_unit": round(num(m["smem_wavefronts"]) / units, 1),
         "smem_bank_conflicts_per_unit": round(num(m["smem_bank_conflicts"]) / units, 2),
         "dram_pct_of_nominal_peak": num(m["dram_pct_of_nominal"]),
-        "source": "profiles/r2_%s_ncu_full.txt (ncu --set full --clock-control none)" % key,
+        "source": "profiles/%s%s_ncu_full.txt (ncu --set full --clock-control none)" % (os.environ.get("PROFILE_PREFIX", "r2_"), key),
     }
 json.dump(res, open(out, "w"), indent=1)
 print("wrote", out, "with", len(res), "kernels")
