@@ -11,6 +11,7 @@
 
 #include "ofdm_chain.cuh"
 #include "ofdm_stream.cuh"
+#include "ofdm_mc_quad.cuh"
 #include "ofdm_sweep.cuh"
 
 using namespace ofdm;
@@ -1042,9 +1043,22 @@ int mc_awgn_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_frames, i
                 k<<<grid, kThreads, smem, ctx->stream>>>(p);
                 return check_launch(ctx, "k_mc_philox");
             };
+            // one frame per lane group (k_mc_quad, ofdm_mc_quad.cuh) for the speculating arithmetic; "stream_layout" = 1 and the
+            // all-exact arithmetic keep the one-frame-per-warp kernel
+            auto launch_quad = [&](auto k) -> int {
+                const size_t qsmem = mc_quad_smem_bytes();
+                OFDM_CUDA(ctx, allow_smem(ctx, k, qsmem));
+                int per_sm = 1;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kMcQuadWarps * 32, qsmem) != cudaSuccess || per_sm < 1) per_sm = 1;
+                const long full = (long)per_sm * ctx->sm_count, need = (p.n_frames + kMcQuadWarps * 4 - 1) / (kMcQuadWarps * 4);
+                const long grid = need < full ? need : full;
+                k<<<(int)(grid < 1 ? 1 : grid), kMcQuadWarps * 32, qsmem, ctx->stream>>>(p);
+                return check_launch(ctx, "k_mc_quad");
+            };
             int st;
-            if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast>);
-            else if (ctx->checked) st = launch(k_mc_philox<kArithChecked>);
+            const bool quad = ctx->stream_layout == 0;
+            if (mode != OFDM_MODE_EXACT) st = quad ? launch_quad(k_mc_quad<kArithFast>) : launch(k_mc_philox<kArithFast>);
+            else if (ctx->checked) st = quad ? launch_quad(k_mc_quad<kArithChecked>) : launch(k_mc_philox<kArithChecked>);
             else st = launch(k_mc_philox<kArithExact>);
             if (st) return st;
         }

@@ -226,7 +226,7 @@ def test_monte_carlo_kernel_checked(knobs, pkg):
     for x, y, z in zip(runs["checked"][0], runs["all_exact"][0], runs["replay_all"][0]):
         assert ints(x) == ints(y) == ints(z)
         assert abs(x.sum_err2 - y.sum_err2) <= 1e-5 * y.sum_err2
-        assert abs(z.sum_err2 - y.sum_err2) <= 1e-12 * y.sum_err2
+        assert abs(z.sum_err2 - y.sum_err2) <= 1e-6 * y.sum_err2          # same per-bin arithmetic, the float terms of a frame added in another order
     assert runs["replay_all"][1] == n * len(snr) and runs["all_exact"][1] == 0
     assert 0 < runs["checked"][1] < n * len(snr) // 10
 
