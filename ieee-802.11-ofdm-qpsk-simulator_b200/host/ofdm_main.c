@@ -128,8 +128,18 @@ static int sweep_multi_gpu(int n_gpus, unsigned seed, long frames, int n_sym, in
         if (n_taps > 0) CHECK(ofdm_mc_sweep_multipath_dev(ctx, seed, 0, 256, n_sym, n_taps, SNR, n_snr, mode, (ofdm_counters *)cnt[d]));
         else CHECK(ofdm_mc_sweep_philox_dev(ctx, seed, 0, 256, n_sym, SNR, n_snr, mode, (ofdm_counters *)cnt[d]));
         CHECK(ofdm_memset_dev(ctx, cnt[d], 0, sizeof(ofdm_counters) * (size_t)n_snr));
+        CHECK(ofdm_counters_pack(ctx, (const ofdm_counters *)cnt[d], n_snr, (uint64_t *)ints[d], (double *)dbls[d]));
         CHECK(ofdm_ctx_sync(ctx));
     }
+    /* ... and so does the first collective of a communicator (NCCL connects its peers lazily: ~0.1 s on 8 GPUs): one all-reduce
+     * of the zeroed buffers before the clock starts */
+    NCHECK(ncclGroupStart());
+    for (int d = 0; d < n_gpus; ++d) {
+        NCHECK(ncclAllReduce(ints[d], ints[d], 5 * (size_t)n_snr, ncclUint64, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+        NCHECK(ncclAllReduce(dbls[d], dbls[d], 3 * (size_t)n_snr, ncclDouble, ncclSum, comms[d], (cudaStream_t)ofdm_ctx_stream(ctxs[d])));
+    }
+    NCHECK(ncclGroupEnd());
+    for (int d = 0; d < n_gpus; ++d) { ctx = ctxs[d]; CHECK(ofdm_ctx_sync(ctx)); }
     if (target_errors > 0) {
         /* configs[3]'s stop rule, sharded as (SNR point x frame range): every GPU works on every still-active point, on its
          * slice of the round's frames; one all-reduce per buffer type per round; identical stop decisions everywhere */
