@@ -113,6 +113,15 @@ int grid_for(ofdm_ctx *ctx, K kernel, size_t dyn_smem, long work_items_per_block
     return (int)(g < 1 ? 1 : g);
 }
 
+// grid of a memory-bound grid-stride kernel: enough blocks to fill the chip (`per_sm` resident blocks per SM) and no more --
+// HBM likes a few hundred concurrent streams, not thousands (k_fft64<fast> at 5 blocks per SM: 5.7 TB/s, at 3: 6.5 TB/s)
+int stream_grid(ofdm_ctx *ctx, long rows, int rows_per_block, int per_sm)
+{
+    const long need = (rows + rows_per_block - 1) / rows_per_block, full = (long)per_sm * ctx->sm_count;
+    const long g = need < full ? need : full;
+    return (int)(g < 1 ? 1 : g);
+}
+
 int ensure_scratch(ofdm_ctx *ctx, int slot, size_t bytes, void **out)
 {
     if (ctx->scratch_bytes[slot] < bytes) {
@@ -192,6 +201,8 @@ int launch_fft(ofdm_ctx *ctx, const float *in, float *out, long n)
 {
     auto k = k_fft64<EXACT, INV>;
     int grid = grid_for(ctx, k, 0, kWarpsPerBlock * 4, n);
+    const int cap = stream_grid(ctx, n, kWarpsPerBlock * 4, 3);       // the fp32 variants' registers would allow 5 blocks per SM
+    if (grid > cap) grid = cap;
     k<<<grid, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), n);
     return check_launch(ctx, "k_fft64");
 }
@@ -615,8 +626,10 @@ int ofdm_qpsk_modulate(ofdm_ctx *ctx, const uint32_t *bits, float *mod, long n_s
     OFDM_REQUIRE(ctx, n_symbols >= 0);
     if (n_symbols == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, bits != nullptr && mod != nullptr);
-    long n = n_symbols * 48;
-    k_qpsk_mod<<<blocks_1d(n), 256, 0, ctx->stream>>>(bits, reinterpret_cast<float2 *>(mod), n);
+    if ((uintptr_t)mod % 16 == 0)
+        k_qpsk_mod2<<<stream_grid(ctx, n_symbols, 2 * kRows4, 6), 2 * kRows4 * 24, 0, ctx->stream>>>(bits, reinterpret_cast<float4 *>(mod), n_symbols);
+    else
+        k_qpsk_mod<<<stream_grid(ctx, n_symbols, kRows4, 6), kRows4 * 48, 0, ctx->stream>>>(bits, reinterpret_cast<float2 *>(mod), n_symbols);
     return check_launch(ctx, "k_qpsk_mod");
 }
 int ofdm_map_subcarriers(ofdm_ctx *ctx, const float *mod, float *grid, long n_symbols)
@@ -625,8 +638,7 @@ int ofdm_map_subcarriers(ofdm_ctx *ctx, const float *mod, float *grid, long n_sy
     OFDM_REQUIRE(ctx, n_symbols >= 0);
     if (n_symbols == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, mod != nullptr && grid != nullptr);
-    long n = n_symbols * 64;
-    k_map_subcarriers<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(mod), reinterpret_cast<float2 *>(grid), n);
+    k_map_subcarriers<<<stream_grid(ctx, n_symbols, kRows4, 4), kRows4 * 64, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(mod), reinterpret_cast<float2 *>(grid), n_symbols);
     return check_launch(ctx, "k_map_subcarriers");
 }
 int ofdm_ifft64(ofdm_ctx *ctx, const float *in, float *out, long n, int mode)
@@ -651,7 +663,7 @@ int ofdm_add_cp(ofdm_ctx *ctx, const float *sym, float *out, long n)
     OFDM_REQUIRE(ctx, n >= 0);
     if (n == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, sym != nullptr && out != nullptr);
-    k_add_cp<<<blocks_1d(n * 80), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(sym), reinterpret_cast<float2 *>(out), n * 80);
+    k_add_cp<<<stream_grid(ctx, n, kRows4, 4), kRows4 * 80, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(sym), reinterpret_cast<float2 *>(out), n);
     return check_launch(ctx, "k_add_cp");
 }
 int ofdm_lts(ofdm_ctx *ctx, float *lts_freq_host, float *lts_time_host)
@@ -808,8 +820,7 @@ int ofdm_strip_cp(ofdm_ctx *ctx, const float *frames, float *bodies, long n_fram
     OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && data_off >= 0 && frame_len >= data_off + 80 * n_sym);
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, frames != nullptr && bodies != nullptr && frames != bodies);
-    const long n = n_frames * n_sym * 64;
-    k_strip_cp<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), reinterpret_cast<float2 *>(bodies), n, n_sym, frame_len, data_off);
+    k_strip_cp<<<stream_grid(ctx, n_frames, kWarpsPerBlock, 4), kThreads, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(frames), reinterpret_cast<float2 *>(bodies), n_frames, n_sym, frame_len, data_off);
     return check_launch(ctx, "k_strip_cp");
 }
 int ofdm_channel_estimate(ofdm_ctx *ctx, const float *frames, float *H, long n_frames, int frame_len, int lts_off, int mode)
@@ -835,11 +846,11 @@ int ofdm_equalize(ofdm_ctx *ctx, const float *F, const float *H, float *E, long 
     OFDM_REQUIRE(ctx, n_frames >= 0 && nsym_ok(n_sym) && mode_ok(mode));
     if (n_frames == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, F != nullptr && H != nullptr && E != nullptr);
-    const long n = n_frames * n_sym * 64;
+    const int grid = stream_grid(ctx, n_frames, kWarpsPerBlock, 4);
     if (mode == OFDM_MODE_EXACT)
-        k_equalize<true><<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(F), reinterpret_cast<const float2 *>(H), reinterpret_cast<float2 *>(E), n, n_sym);
+        k_equalize<true><<<grid, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(F), reinterpret_cast<const float2 *>(H), reinterpret_cast<float2 *>(E), n_frames, n_sym);
     else
-        k_equalize<false><<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(F), reinterpret_cast<const float2 *>(H), reinterpret_cast<float2 *>(E), n, n_sym);
+        k_equalize<false><<<grid, kThreads, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(F), reinterpret_cast<const float2 *>(H), reinterpret_cast<float2 *>(E), n_frames, n_sym);
     return check_launch(ctx, "k_equalize");
 }
 int ofdm_demap(ofdm_ctx *ctx, const float *grid, float *points, long n_symbols)
@@ -848,8 +859,7 @@ int ofdm_demap(ofdm_ctx *ctx, const float *grid, float *points, long n_symbols)
     OFDM_REQUIRE(ctx, n_symbols >= 0);
     if (n_symbols == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, grid != nullptr && points != nullptr && grid != points);
-    const long n = n_symbols * 48;
-    k_demap<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(grid), reinterpret_cast<float2 *>(points), n);
+    k_demap<<<stream_grid(ctx, n_symbols, kRows4, 6), kRows4 * 48, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(grid), reinterpret_cast<float2 *>(points), n_symbols);
     return check_launch(ctx, "k_demap");
 }
 int ofdm_agc_slicer(ofdm_ctx *ctx, const float *points, float *sliced, long n_symbols)
@@ -859,7 +869,10 @@ int ofdm_agc_slicer(ofdm_ctx *ctx, const float *points, float *sliced, long n_sy
     if (n_symbols == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, points != nullptr && sliced != nullptr);
     const long n = n_symbols * 48;
-    k_agc_slicer<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(points), reinterpret_cast<float2 *>(sliced), n);
+    if (((uintptr_t)points | (uintptr_t)sliced) % 16 == 0)            // n is even: 48 points per symbol
+        k_agc_slicer2<<<stream_grid(ctx, n / 2, kThreads, 4), kThreads, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(points), reinterpret_cast<float4 *>(sliced), n / 2);
+    else
+        k_agc_slicer<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(points), reinterpret_cast<float2 *>(sliced), n);
     return check_launch(ctx, "k_agc_slicer");
 }
 int ofdm_qpsk_demodulate(ofdm_ctx *ctx, const float *points, uint32_t *bits, long n_symbols)
@@ -869,7 +882,10 @@ int ofdm_qpsk_demodulate(ofdm_ctx *ctx, const float *points, uint32_t *bits, lon
     if (n_symbols == 0) return OFDM_OK;
     OFDM_REQUIRE(ctx, points != nullptr && bits != nullptr);
     const long n = n_symbols * 3;
-    k_qpsk_demod<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(points), bits, n);
+    if ((uintptr_t)points % 16 == 0)
+        k_qpsk_demod_warp<<<stream_grid(ctx, (n + 31) / 32, kWarpsPerBlock, 4), kThreads, 0, ctx->stream>>>(reinterpret_cast<const float4 *>(points), bits, n);
+    else
+        k_qpsk_demod<<<blocks_1d(n), 256, 0, ctx->stream>>>(reinterpret_cast<const float2 *>(points), bits, n);
     return check_launch(ctx, "k_qpsk_demod");
 }
 

@@ -30,37 +30,50 @@ __global__ void k_unpack_bits(const uint32_t *__restrict__ packed, uint8_t *__re
     bits[i] = (uint8_t)((packed[i >> 5] >> (i & 31)) & 1u);
 }
 
-// QPSK_Modulator OFDM.c:415-433; one thread per constellation point
-__global__ void k_qpsk_mod(const uint32_t *__restrict__ bits, float2 *__restrict__ mod, long n_points)
+// The element-wise stages below share one shape: a block covers four rows (symbols) per step of a grid-stride loop and a
+// thread keeps its column for the whole launch, so everything that depends only on the column -- which payload word and
+// bit pair, which source bin, which table entry (a lane-varying index into __constant__ memory is read once per thread,
+// not once per element) -- is computed once, nothing divides per element, and every row is read and written as one
+// contiguous run.  Block sizes: 4 x columns (kRows4).
+constexpr int kRows4 = 4;
+
+// QPSK_Modulator OFDM.c:415-433; column = constellation point d of the symbol (block of 4 x 48 threads)
+__global__ void __launch_bounds__(kRows4 * 48) k_qpsk_mod(const uint32_t *__restrict__ bits, float2 *__restrict__ mod, long n_sym_total)
 {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_points) return;
-    long sym = i / 48; int d = (int)(i - sym * 48);
-    const uint32_t *w = bits + sym * 3;
-    mod[i] = qpsk_point(bit_pair(w[0], w[1], w[2], d));
+    const int d = threadIdx.x % 48, r = threadIdx.x / 48;
+    const int word = d >> 4, shift = 2 * (d & 15);
+    for (long sym = (long)blockIdx.x * kRows4 + r; sym < n_sym_total; sym += (long)gridDim.x * kRows4)
+        mod[sym * 48 + d] = qpsk_point((bits[sym * 3 + word] >> shift) & 3u);
+}
+// the same on a 16-byte aligned output: two points per store (block of 4 x 24 threads x 2 row groups)
+__global__ void __launch_bounds__(2 * kRows4 * 24) k_qpsk_mod2(const uint32_t *__restrict__ bits, float4 *__restrict__ mod, long n_sym_total)
+{
+    const int h = threadIdx.x % 24, r = threadIdx.x / 24;           // points 2h, 2h + 1 of the symbol
+    const int word = h >> 3, shift = 4 * (h & 7);
+    for (long sym = (long)blockIdx.x * (2 * kRows4) + r; sym < n_sym_total; sym += (long)gridDim.x * (2 * kRows4)) {
+        const uint32_t q = bits[sym * 3 + word] >> shift;
+        const float2 a = qpsk_point(q & 3u), b = qpsk_point((q >> 2) & 3u);
+        mod[sym * 24 + h] = make_float4(a.x, a.y, b.x, b.y);
+    }
 }
 
-// frame-build block OFDM.c:523-548; one thread per grid bin (centred index c)
-__global__ void k_map_subcarriers(const float2 *__restrict__ mod, float2 *__restrict__ grid, long n_bins)
+// frame-build block OFDM.c:523-548; column = grid bin (centred index c) (block of 4 x 64 threads)
+__global__ void __launch_bounds__(kRows4 * 64) k_map_subcarriers(const float2 *__restrict__ mod, float2 *__restrict__ grid, long n_sym_total)
 {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_bins) return;
-    long sym = i >> 6; int c = (int)(i & 63);
-    int d = c_tab.bin_data[(c + 32) & 63];
-    float2 v = make_float2(0.f, 0.f);
-    if (d >= 0) v = mod[sym * 48 + d];
-    else if (d == -2) v.x = 1.f;
-    else if (d == -3) v.x = -1.f;
-    grid[i] = v;
+    const int c = threadIdx.x & 63, r = threadIdx.x >> 6;
+    const int d = c_tab.bin_data[(c + 32) & 63];
+    const float2 fixed = make_float2(d == -2 ? 1.f : (d == -3 ? -1.f : 0.f), 0.f);            // pilots {1,1,1,-1} :523, nulls
+    for (long sym = (long)blockIdx.x * kRows4 + r; sym < n_sym_total; sym += (long)gridDim.x * kRows4)
+        grid[sym * 64 + c] = d >= 0 ? mod[sym * 48 + d] : fixed;
 }
 
-// CP add OFDM.c:559-565
-__global__ void k_add_cp(const float2 *__restrict__ sym, float2 *__restrict__ out, long n_out)
+// CP add OFDM.c:559-565; column = output sample k of the 80 (block of 4 x 80 threads)
+__global__ void __launch_bounds__(kRows4 * 80) k_add_cp(const float2 *__restrict__ sym, float2 *__restrict__ out, long n_sym_total)
 {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
-    long s = i / 80; int k = (int)(i - s * 80);
-    out[i] = sym[s * 64 + (k < 16 ? 48 + k : k - 16)];
+    const int k = threadIdx.x % 80, r = threadIdx.x / 80;
+    const int src = k < 16 ? 48 + k : k - 16;
+    for (long s = (long)blockIdx.x * kRows4 + r; s < n_sym_total; s += (long)gridDim.x * kRows4)
+        out[s * 80 + k] = sym[s * 64 + src];
 }
 
 // ------------------------------------------------------------------ stand-alone transforms
@@ -685,13 +698,16 @@ __global__ void __launch_bounds__(kThreads, DUMP ? 1 : 2) k_rx_frames(RxParams p
 
 // CP strip OFDM.c:1024-1031: frames [n][frame_len] -> symbol bodies [n][n_sym][64]; data_off = sample index of the
 // first data symbol (160 for LTS || data frames, 320 with the STS slot in front as in the reference's own frame)
-__global__ void k_strip_cp(const float2 *__restrict__ frames, float2 *__restrict__ out, long n_out, int n_sym, int frame_len, int data_off)
+// (one warp per frame: 32 consecutive samples per access, no division per element)
+__global__ void __launch_bounds__(kThreads) k_strip_cp(const float2 *__restrict__ frames, float2 *__restrict__ out, long n_frames, int n_sym, int frame_len, int data_off)
 {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
-    const long per = (long)n_sym * 64;
-    const long f = i / per; const int r = (int)(i - f * per), s = r >> 6, k = r & 63;
-    out[i] = frames[f * frame_len + data_off + 80 * s + 16 + k];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = n_sym * 64;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float2 *x = frames + f * frame_len + data_off + 16;
+        float2 *y = out + f * per;
+        for (int idx = lane; idx < per; idx += 32) y[idx] = x[80 * (idx >> 6) + (idx & 63)];
+    }
 }
 
 // Channel_Estimation OFDM.c:830-850: fft of the two LTS halves (samples lts_off + 32 .. + 95 and + 96 .. + 159 of each
@@ -770,23 +786,30 @@ __device__ __forceinline__ float2 divsc3(float2 n, float2 h)
 
 // one-tap equaliser OFDM.c:1044-1052: E[f][s][c] = F[f][s][c] / H[f][c] for all 64 centred bins (the 12 null bins
 // come out as the inf / NaN the reference computes there and never reads -- SURVEY Q16)
+// (one warp per frame: the estimate's two bins per lane are read once and serve all the frame's symbols)
 template <bool EXACT>
-__global__ void k_equalize(const float2 *__restrict__ F, const float2 *__restrict__ H, float2 *__restrict__ E, long n_total, int n_sym)
+__global__ void __launch_bounds__(kThreads) k_equalize(const float2 *__restrict__ F, const float2 *__restrict__ H, float2 *__restrict__ E, long n_frames, int n_sym)
 {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_total) return;
-    const long f = i / ((long)n_sym * 64);
-    const float2 h = H[f * 64 + (i & 63)];
-    E[i] = EXACT ? divsc3(F[i], h) : div_fast(F[i], h);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long f = (long)blockIdx.x * kWarpsPerBlock + warp; f < n_frames; f += (long)gridDim.x * kWarpsPerBlock) {
+        const float2 h0 = H[f * 64 + lane], h1 = H[f * 64 + 32 + lane];
+        const float2 *x = F + f * n_sym * 64;
+        float2 *y = E + f * n_sym * 64;
+        for (int s = 0; s < n_sym; ++s) {
+            const float2 a = x[s * 64 + lane], b = x[s * 64 + 32 + lane];
+            y[s * 64 + lane] = EXACT ? divsc3(a, h0) : div_fast(a, h0);
+            y[s * 64 + 32 + lane] = EXACT ? divsc3(b, h1) : div_fast(b, h1);
+        }
+    }
 }
 
-// demap OFDM.c:1059-1069: the 48 data bins of each centred 64-grid, in order
-__global__ void k_demap(const float2 *__restrict__ grid, float2 *__restrict__ out, long n_points)
+// demap OFDM.c:1059-1069: the 48 data bins of each centred 64-grid, in order; column = data index d (block of 4 x 48 threads)
+__global__ void __launch_bounds__(kRows4 * 48) k_demap(const float2 *__restrict__ grid, float2 *__restrict__ out, long n_sym_total)
 {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_points) return;
-    const long sym = i / 48; const int d = (int)(i - sym * 48);
-    out[i] = grid[sym * 64 + ((c_tab.data_bin[d] + 32) & 63)];
+    const int d = threadIdx.x % 48, r = threadIdx.x / 48;
+    const int src = (c_tab.data_bin[d] + 32) & 63;
+    for (long sym = (long)blockIdx.x * kRows4 + r; sym < n_sym_total; sym += (long)gridDim.x * kRows4)
+        out[sym * 48 + d] = grid[sym * 64 + src];
 }
 
 // AGC_Receiver OFDM.c:852-871: the hard-decision slicer -- each rail to +1/sqrt(2) if > 0 else -1/sqrt(2) (0 and NaN go negative)
@@ -797,9 +820,54 @@ __global__ void k_agc_slicer(const float2 *__restrict__ in, float2 *__restrict__
     const float2 z = in[i];
     out[i] = make_float2(z.x > 0.f ? kQpsk : -kQpsk, z.y > 0.f ? kQpsk : -kQpsk);
 }
+// the same on 16-byte aligned buffers: two points per access, grid-stride
+__global__ void __launch_bounds__(kThreads) k_agc_slicer2(const float4 *__restrict__ in, float4 *__restrict__ out, long n_pairs)
+{
+    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < n_pairs; i += (long)gridDim.x * kThreads) {
+        const float4 z = in[i];
+        out[i] = make_float4(z.x > 0.f ? kQpsk : -kQpsk, z.y > 0.f ? kQpsk : -kQpsk, z.z > 0.f ? kQpsk : -kQpsk, z.w > 0.f ? kQpsk : -kQpsk);
+    }
+}
 
 // QPSK_Demodulator OFDM.c:873-908 with the reference's own comparisons: (+,+) -> 00, (-,+) -> 01, (-,-) -> 10, anything else
 // (a zero or NaN rail included) -> 11; bit 2j = c, bit 2j+1 = d.  One thread per packed word (16 points).
+__device__ __forceinline__ uint32_t demod_point(float a, float b)
+{
+    uint32_t c, d;
+    if (a > 0.f && b > 0.f) { c = 0; d = 0; }
+    else if (a < 0.f && b > 0.f) { c = 0; d = 1; }
+    else if (a < 0.f && b < 0.f) { c = 1; d = 0; }
+    else { c = 1; d = 1; }
+    return c | (d << 1);
+}
+// 16-byte aligned input: a warp turns 512 points (4 KB, coalesced 16-byte loads) into 32 words.  Load k of a lane holds points
+// 64 k + 2 lane and + 1, i.e. bits 4 (lane & 7) .. + 3 of word 4 k + (lane >> 3); the eight lanes of a group OR their nibbles.
+__global__ void __launch_bounds__(kThreads) k_qpsk_demod_warp(const float4 *__restrict__ in, uint32_t *__restrict__ bits, long n_words)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long n_chunks = (n_words + 31) / 32;
+    for (long ch = (long)blockIdx.x * kWarpsPerBlock + warp; ch < n_chunks; ch += (long)gridDim.x * kWarpsPerBlock) {
+        const float4 *src = in + ch * 256 + lane;                    // 256 float4 = 512 points per chunk
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const long w = ch * 32 + 4 * k + (lane >> 3);
+            uint32_t v = 0;
+            if (w < n_words) {
+                const float4 z = src[32 * k];
+                v = (demod_point(z.x, z.y) | (demod_point(z.z, z.w) << 2)) << (4 * (lane & 7));
+            }
+            v |= __shfl_xor_sync(0xffffffffu, v, 1);
+            v |= __shfl_xor_sync(0xffffffffu, v, 2);
+            v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            // word 4 k + g is complete in the lanes of group g: lane 4 k + g keeps it, so that lane L ends up with word L of the chunk
+            const uint32_t got = __shfl_sync(0xffffffffu, v, 8 * (lane & 3));
+            if ((lane >> 2) == k) mine = got;
+        }
+        const long w = ch * 32 + lane;
+        if (w < n_words) bits[w] = mine;
+    }
+}
 __global__ void k_qpsk_demod(const float2 *__restrict__ in, uint32_t *__restrict__ bits, long n_words)
 {
     const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
