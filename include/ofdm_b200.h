@@ -101,7 +101,12 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *                            speculating in fp32, verifying, and replaying doubtful frames exactly (default 1;
  *                            both give the same error counts)
  *   "force_replay"      = 1  the verification fails on every frame (exercises the replay path)
- *   "general_stream"    = 1  two-symbol frames also take the multi-pass streaming kernel that serves every other frame shape
+ *   "stream_layout"     = 1  the fused receivers and the fused Monte-Carlo sweep give a warp one frame at a time (k_stream_rx2 /
+ *                            k_stream_rxn / k_mc_philox) instead of one frame per 8-lane group (k_stream_quad / k_mc_quad,
+ *                            default 0; same totals in EXACT mode, DESIGN.md sections 4.5, 4.6)
+ *   "stream_warps"      = 8  k_stream_quad in blocks of 8 warps (128 registers) instead of 6 (168 registers, default)
+ *   "general_stream"    = 1  with "stream_layout" = 1: two-symbol frames also take the multi-pass streaming kernel that serves
+ *                            every other frame shape
  *   "evm_guard"         = N  bins whose channel estimate is smaller than N error radii are replayed exactly (default 820): the
  *                            EVM sums' distance from the all-exact kernel's against the number of replays
  *   "power_margin"      = N  the exact frame power speculates each term of the serial float sum as x^2 + y^2 and takes the
