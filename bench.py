@@ -429,15 +429,15 @@ def run_configs(o, pkg, torch, dist, dev, args, rank, world):
             assert all(t.frames == world * nm and t.bits == world * nm * 96 * N_SYM for t in tot), "all-reduced totals"
             sym = world * nm * N_SYM * len(SNRS) / (ms * 1e-3)
             c[name] = {"ms": ms, "symbols_per_s": sym, "symbols_per_s_per_gpu": sym / world,
-                       # transforms actually executed per frame and SNR point: three with one frame per lane group (the LTS halves are added
-                       # in time), four in the one-frame-per-warp multipath kernel; 1920 flop per 64-point transform
-                       "fft_tflops_per_gpu": nm * len(SNRS) * (4 if n_taps and name == "fast" else 3) * 1920 / (ms * 1e-3) / 1e12,
+                       # transforms actually executed per frame and SNR point: three (one frame per lane group, the LTS halves are added
+                       # in time); 1920 flop per 64-point transform
+                       "fft_tflops_per_gpu": nm * len(SNRS) * 3 * 1920 / (ms * 1e-3) / 1e12,
                        "ber_0_10_14dB": [tot[0].bit_errors / tot[0].bits, tot[10].bit_errors / tot[10].bits, tot[14].bit_errors / tot[14].bits],
                        "roofline": dict({"bound": "issue (on-chip: no HBM traffic beyond the counters)",
-                                         "kernel": ("k_mc_philox<%s,multipath>" % name if n_taps and name == "fast" else
+                                         "kernel": ("k_mc_quad<fast,multipath>" if n_taps and name == "fast" else
                                                     "staged: k_tx_frames2 + k_multipath + k_frame_power + k_stream_quad<checked,philox> per point" if n_taps else
                                                     "k_mc_quad<%s>" % ("fast" if name == "fast" else "checked"))},
-                                        **km.get("k_mc_philox_fast_multipath" if n_taps and name == "fast" else
+                                        **km.get("k_mc_quad_fast_multipath" if n_taps and name == "fast" else
                                                  "k_mc_quad_%s" % ("fast" if name == "fast" else "checked") if not n_taps else "", {}))}
         out[key] = c
 

@@ -1259,7 +1259,18 @@ int mc_multipath_core(ofdm_ctx *ctx, uint32_t seed, uint64_t frame0, long n_fram
                 return check_launch(ctx, "k_mc_philox<multipath>");
             };
             int st;
-            if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast, true>);
+            if (mode != OFDM_MODE_EXACT && ctx->stream_layout == 0) {           // one frame per lane group (k_mc_quad<fast, multipath>)
+                auto k = k_mc_quad<kArithFast, true>;
+                const size_t qsmem = mc_quad_mp_smem_bytes();
+                OFDM_CUDA(ctx, allow_smem(ctx, k, qsmem));
+                int per_sm = 1;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kMcQuadWarps * 32, qsmem) != cudaSuccess || per_sm < 1) per_sm = 1;
+                const long full = (long)per_sm * ctx->sm_count, need = (p.n_frames + kMcQuadWarps * 4 - 1) / (kMcQuadWarps * 4);
+                const long grid = need < full ? need : full;
+                k<<<(int)(grid < 1 ? 1 : grid), kMcQuadWarps * 32, qsmem, ctx->stream>>>(p);
+                st = check_launch(ctx, "k_mc_quad<multipath>");
+            }
+            else if (mode != OFDM_MODE_EXACT) st = launch(k_mc_philox<kArithFast, true>);
             else if (ctx->checked) st = launch(k_mc_philox<kArithChecked, true>);
             else st = launch(k_mc_philox<kArithExact, true>);
             if (st) return st;

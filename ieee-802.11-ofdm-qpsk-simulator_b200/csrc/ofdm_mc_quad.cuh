@@ -31,18 +31,36 @@ struct alignas(16) McQuadWarp {
 };
 inline size_t mc_quad_smem_bytes() { return sizeof(McQuadWarp) * kMcQuadWarps + 2 * kWin * sizeof(float2); }
 
-template <int ARITH>
+// configs[4] fused the same way (fp32 arithmetic only: the verified multipath sweep is faster staged through HBM):
+// per-frame random taps (Philox domain 2, as k_multipath<true>) applied by the frame's lane group to its own 320 samples, in
+// k_multipath's operation order; the power is that of the faded frame; the faded LTS halves go to fwl, the faded symbol
+// bodies replace the clean ones in place, last symbol first (a symbol's faded samples depend on nothing after it: n_taps <= 16).
+struct alignas(16) McQuadWarpMp {
+    float2 tile[kWarpTile];
+    float2 body[4][2 * kWin + 8];       // clean, then faded symbol bodies
+    float2 fwl[4][2 * kWin + 8];        // faded LTS halves
+    float2 taps[4][kMaxTaps];
+    float2 stage[4][96];                // 15 samples of history + the 80 clean samples (CP + body) of the symbol being faded, contiguous
+    uint2 res[4][kMaxSnr];
+};
+inline size_t mc_quad_mp_smem_bytes() { return sizeof(McQuadWarpMp) * kMcQuadWarps + 160 * sizeof(float2); }
+template <bool MP> struct McQuadSmem { using type = McQuadWarp; };
+template <> struct McQuadSmem<true> { using type = McQuadWarpMp; };
+
+template <int ARITH, bool MP = false>
 __global__ void __launch_bounds__(kMcQuadWarps * 32, 2) k_mc_quad(McParams p)
 {
     static_assert(ARITH == kArithFast || ARITH == kArithChecked, "the all-exact arithmetic runs in k_mc_philox");
+    static_assert(!MP || ARITH == kArithFast, "the fused multipath variant is fp32 only");
     constexpr bool CHECKED = ARITH == kArithChecked;
     constexpr int LEVEL = CHECKED ? 2 : 0;                        // fast: plain fp32 (statistical results, no EVM guard: as k_mc_philox)
     constexpr int WARPS = kMcQuadWarps;
     extern __shared__ __align__(128) unsigned char s_raw[];
-    McQuadWarp *ws_all = reinterpret_cast<McQuadWarp *>(s_raw);
-    float2 *s_ltsx = reinterpret_cast<float2 *>(s_raw + sizeof(McQuadWarp) * WARPS);           // [2][kWin]: the LTS halves in time
+    using WS = typename McQuadSmem<MP>::type;
+    WS *ws_all = reinterpret_cast<WS *>(s_raw);
+    float2 *s_ltsx = reinterpret_cast<float2 *>(s_raw + sizeof(WS) * WARPS);    // [2][kWin]: the LTS halves in time; MP: the whole 160-sample LTS slot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3, u = lane & 7;
-    McQuadWarp &ws = ws_all[warp];
+    WS &ws = ws_all[warp];
     float2 *tile = ws.tile + grp * kGroupPitch;
     Tw<false> tw; tw.load(u);
     const QuadLane ql = make_quad_lane(u);
@@ -50,7 +68,8 @@ __global__ void __launch_bounds__(kMcQuadWarps * 32, 2) k_mc_quad(McParams p)
     int dmap_tx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dmap_tx[i] = c_tab.bin_data[8 * slot_m<CHECKED>(i) + u];
-    for (int i = threadIdx.x; i < 128; i += WARPS * 32) s_ltsx[(i >> 6) * kWin + (i & 63)] = c_tab.lts_time[32 + i];
+    if constexpr (MP) { for (int i = threadIdx.x; i < 160; i += WARPS * 32) s_ltsx[i] = c_tab.lts_time[i]; }
+    else { for (int i = threadIdx.x; i < 128; i += WARPS * 32) s_ltsx[(i >> 6) * kWin + (i & 63)] = c_tab.lts_time[32 + i]; }
     __syncthreads();
 
     const double q = (double)kQpsk;
@@ -100,7 +119,61 @@ __global__ void __launch_bounds__(kMcQuadWarps * 32, 2) k_mc_quad(McParams p)
         }
         __syncwarp();
         float P;
-        if constexpr (CHECKED) {
+        if constexpr (MP) {
+            // taps of this frame (k_multipath<true>): i.i.d. complex Gaussian, E|h_l|^2 = 1 / n_taps
+            const int n_taps = p.n_taps;
+            if (2 * u < n_taps) {
+                const float scale = sqrtf(0.5f / (float)n_taps);
+                float z[4];
+                philox_normals4(p.seed, 0u, fr, (uint32_t)u, kDomainTaps, z);
+                ws.taps[grp][2 * u] = make_float2(scale * z[0], scale * z[1]);
+                if (2 * u + 1 < n_taps) ws.taps[grp][2 * u + 1] = make_float2(scale * z[2], scale * z[3]);
+            }
+            __syncwarp();
+            // clean frame sample n: the LTS slot, then (CP + body) x 2 (:559-581)
+            auto clean = [&](int n) -> float2 {
+                if (n < 160) return s_ltsx[n];
+                const int s = n >= 240 ? 1 : 0, k = n - 160 - 80 * s;
+                return ws.body[grp][s * kWin + (k < 16 ? 48 + k : k - 16)];
+            };
+            // y[n] = sum_l h[l] x[n-l], descending l, separate multiplies and adds (k_multipath's order), on a contiguous run of
+            // clean samples: x[0] = the sample at the output's own position
+            auto fir = [&](const float2 *x, int l_max) -> float2 {
+                float ar = 0.f, ai = 0.f;
+                for (int l = l_max; l >= 0; --l) {
+                    const float2 a = x[-l], b = ws.taps[grp][l];
+                    ar = __fadd_rn(ar, __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)));
+                    ai = __fadd_rn(ai, __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+                }
+                return make_float2(ar, ai);
+            };
+            float pm = 0.f;
+            for (int n = u; n < 160; n += 8) {                      // the LTS slot: guard interval (power only), then the two halves
+                const float2 y = fir(s_ltsx + n, n_taps - 1 < n ? n_taps - 1 : n);
+                pm = fmaf(y.x, y.x, fmaf(y.y, y.y, pm));
+                if (n >= 32) ws.fwl[grp][((n - 32) >> 6) * kWin + ((n - 32) & 63)] = y;
+            }
+            // symbol 1 first: its cyclic prefix still needs the clean tail of symbol 0 (the taps reach 15 samples back), while
+            // symbol 0 depends on nothing after itself
+#pragma unroll 1
+            for (int s = 1; s >= 0; --s) {
+                float2 *st = ws.stage[grp];
+                for (int i = u; i < 95; i += 8) st[i] = clean(145 + 80 * s + i);
+                __syncwarp();                                     // ... after which nobody reads the clean symbol any more
+                // lane u: samples k = u + 8 m of the symbol; m < 2 is the CP (power only), the rest its own share of the body
+#pragma unroll 1
+                for (int m = 0; m < 10; ++m) {
+                    const float2 y = fir(st + 15 + u + 8 * m, n_taps - 1);
+                    pm = fmaf(y.x, y.x, fmaf(y.y, y.y, pm));
+                    if (m >= 2) ws.body[grp][s * kWin + u + 8 * (m - 2)] = y;
+                }
+                __syncwarp();
+            }
+            pm += __shfl_xor_sync(0xffffffffu, pm, 1);
+            pm += __shfl_xor_sync(0xffffffffu, pm, 2);
+            pm += __shfl_xor_sync(0xffffffffu, pm, 4);
+            P = pm / 320.f;
+        } else if constexpr (CHECKED) {
             // OFDM.c:637-643 on the 320-sample frame: the LTS prefix is a constant, the 160 data samples follow in order.  The
             // terms are speculated as x^2 + y^2 in double by the group's eight lanes; lane 0 runs the sequential float chain over
             // them and takes glibc's hypot()^2 only where the running sum is within 16 double ulps of a float tie (power_step,
@@ -159,7 +232,8 @@ __global__ void __launch_bounds__(kMcQuadWarps * 32, 2) k_mc_quad(McParams p)
                 for (int o = 1; o < 8; o <<= 1) { pk += __shfl_xor_sync(0xffffffffu, pk, o); e2 += __shfl_xor_sync(0xffffffffu, e2, o); }
                 if (u == 0 && si > 0) ws.res[grp][si - 1] = make_uint2(pk, __float_as_uint(e2));
             }
-            const float sigma_f = CHECKED ? ws.sig[grp][si] : sqrtP * p.inv_sqrt_snr[si];
+            float sigma_f;
+            if constexpr (CHECKED) sigma_f = ws.sig[grp][si]; else sigma_f = sqrtP * p.inv_sqrt_snr[si];
             const uint32_t stream = p.stream[si];
             // noisy samples of the window whose Philox blocks start at blk (v[m] = x[u + 8m] + sigma z, real rail only: SURVEY Q1)
             auto window = [&](const float2 *src, int blk, float2 (&v)[8], float2 &n2) {
@@ -182,8 +256,8 @@ __global__ void __launch_bounds__(kMcQuadWarps * 32, 2) k_mc_quad(McParams p)
             {
                 float2 b[8];
                 float2 n2 = make_float2(0.f, 0.f);
-                window(s_ltsx, 8, G, n2);
-                window(s_ltsx + kWin, 24, b, n2);
+                if constexpr (MP) { window(ws.fwl[grp], 8, G, n2); window(ws.fwl[grp] + kWin, 24, b, n2); }
+                else { window(s_ltsx, 8, G, n2); window(s_ltsx + kWin, 24, b, n2); }
 #pragma unroll
                 for (int m = 0; m < 8; ++m) G[m] = cadd(G[m], b[m]);
                 if (CHECKED) rH2 = window_radius(n2, p.radius_scale * 1.41421366f, 2.f * chan);
@@ -233,7 +307,7 @@ __global__ void __launch_bounds__(kMcQuadWarps * 32, 2) k_mc_quad(McParams p)
             }
             uint32_t pk = f_i | (f_q << 8) | (f_both << 16);      // per lane at most 14 of each
             float e2 = e2v.x + e2v.y;
-            if (CHECKED) {
+            if constexpr (CHECKED) {
                 uint32_t dm = __ballot_sync(0xffffffffu, doubt && active);
                 while (dm != 0u) {                                // warp-uniform: the whole warp replays one (frame, point) at a time
                     const int g = (__ffs((int)dm) - 1) >> 3;

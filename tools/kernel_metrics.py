@@ -18,7 +18,7 @@ KERNELS = {   # what -> (key, units per launch, unit name, committed summary)
     "tx_exact": ("k_tx_frames2_exact", N2, "frame"),
     "mc_fast": ("k_mc_quad_fast", N * NS, "frame x SNR point"),
     "mc_exact": ("k_mc_quad_checked", N * NS, "frame x SNR point"),
-    "mp_fast": ("k_mc_philox_fast_multipath", N * NS, "frame x SNR point"),
+    "mp_fast": ("k_mc_quad_fast_multipath", N * NS, "frame x SNR point"),
     "power_full": ("k_frame_power_tiled", N, "frame (320 samples)"),
 }
 

@@ -5,10 +5,10 @@ mkdir -p gpurun_out
 P=gpurun_out/r2b_
 timeout 1500 python -m pytest tests -m gpu -q > ${P}pytest.txt 2>&1; echo "pytest exit $?" >> ${P}pytest.txt; tail -3 ${P}pytest.txt
 timeout 600 python tools/r2_kernels.py all 5 > ${P}kernels.txt 2>&1; echo "kernels exit $?"; cat ${P}kernels.txt
-for k in point point_fast rx_fast rx_exact mc_fast mc_exact; do echo -n "one frame per warp (stream_layout 1)  "; STREAM_LAYOUT=1 timeout 300 python tools/r2_kernels.py $k 5 2>&1 | tail -1; done | tee ${P}kernels_layout1.txt
+for k in point point_fast rx_fast rx_exact mc_fast mc_exact mp_fast; do echo -n "one frame per warp (stream_layout 1)  "; STREAM_LAYOUT=1 timeout 300 python tools/r2_kernels.py $k 5 2>&1 | tail -1; done | tee ${P}kernels_layout1.txt
 for k in point rx_fast rx_exact; do echo -n "8 warps per block (stream_warps 8)  "; STREAM_WARPS=8 timeout 300 python tools/r2_kernels.py $k 5 2>&1 | tail -1; done | tee ${P}kernels_warps8.txt
 timeout 600 python tools/nsym_probe.py > ${P}nsym_probe.txt 2>&1; tail -12 ${P}nsym_probe.txt
-for what in point point_fast rx_fast rx_exact mc_fast mc_exact; do
+for what in point point_fast rx_fast rx_exact mc_fast mc_exact mp_fast; do
   timeout 300 python tools/r2_kernels.py $what 2 > ${P}plain_$what.log 2>&1 || { echo "plain $what failed"; continue; }
   src=""; [ "$what" = "rx_exact" ] && src="--import-source on"
   timeout 600 ncu --set full --clock-control none $src -k 'regex:k_stream_quad|k_mc_quad' -s 1 -c 1 -f -o ${P}prof_$what python tools/r2_kernels.py $what 2 > ${P}ncu_$what.log 2>&1
