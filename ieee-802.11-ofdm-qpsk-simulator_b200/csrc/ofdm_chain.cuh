@@ -1615,7 +1615,8 @@ __global__ void __launch_bounds__(kThreads) k_gather(const float2 *__restrict__ 
         const float2 *src = in + f * in_len;
         float2 *dst = out + f * out_len;
         int idx = (int)(((long)s + lane) % in_len);
-        for (int j = lane; j < out_len; j += 32) {
+#pragma unroll 4
+        for (int j = lane; j < out_len; j += 32) {                  // (unrolled: four loads in flight per lane)
             dst[j] = src[idx];
             idx += step;
             if (idx >= in_len) idx -= in_len;
