@@ -656,13 +656,25 @@ __global__ void __launch_bounds__(kThreads) k_tx_frames2(const uint32_t *__restr
     __syncwarp();
     const int k = grp & 1, sy = grp >> 1;                        // frame of the pair, symbol of the frame (half-warp partners: the two frames)
     const long n_pairs = (n_frames + 1) / 2;
+    const long pr_step = (long)gridDim.x * kWarpsPerBlock;
     uint32_t it = 0;
-    for (long pr = (long)blockIdx.x * kWarpsPerBlock + warp; pr < n_pairs; pr += (long)gridDim.x * kWarpsPerBlock, ++it) {
+    // the payload words of a pass are fetched one pass ahead: they are the first thing a pass needs, and with two resident blocks
+    // per SM (the exact arithmetic's 96 registers) nothing else covered their latency (ncu: long_scoreboard 2.0 per issue)
+    // (the fp32 build runs four blocks per SM at 63 registers and is faster without the three extra registers: 0.92 vs 0.87 of peak)
+    uint32_t nw0 = 0, nw1 = 0, nw2 = 0;
+    if (EXACT) {
+        const long f = 2 * ((long)blockIdx.x * kWarpsPerBlock + warp) + k;
+        if (f < n_frames) { const uint32_t *w = bits + (f * 2 + sy) * 3; nw0 = w[0]; nw1 = w[1]; nw2 = w[2]; }
+    }
+    for (long pr = (long)blockIdx.x * kWarpsPerBlock + warp; pr < n_pairs; pr += pr_step, ++it) {
         const int st = (int)(it & 1u);
         const long f = 2 * pr + k;
-        const bool active = f < n_frames;
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
-        if (active) { const uint32_t *w = bits + (f * 2 + sy) * 3; w0 = w[0]; w1 = w[1]; w2 = w[2]; }
+        uint32_t w0 = nw0, w1 = nw1, w2 = nw2;
+        if (EXACT) {
+            const long fn = f + 2 * pr_step;
+            nw0 = nw1 = nw2 = 0;
+            if (fn < n_frames) { const uint32_t *w = bits + (fn * 2 + sy) * 3; nw0 = w[0]; nw1 = w[1]; nw2 = w[2]; }
+        } else if (f < n_frames) { const uint32_t *w = bits + (f * 2 + sy) * 3; w0 = w[0]; w1 = w[1]; w2 = w[2]; }
         float2 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
