@@ -243,10 +243,10 @@ int launch_stream_n(ofdm_ctx *ctx, const RxParams &p)
     k<<<grid, kThreads, smem, ctx->stream>>>(p);
     return check_launch(ctx, "k_stream_rxn");
 }
-template <int ARITH, int NOISE, int WARPS>
+template <int ARITH, int NOISE, int WARPS, bool NSYM2 = false>
 int launch_stream_quad_w(ofdm_ctx *ctx, const RxParams &p)
 {
-    auto k = k_stream_quad<ARITH, NOISE, WARPS>;
+    auto k = k_stream_quad<ARITH, NOISE, WARPS, NSYM2>;
     const size_t smem = quad_smem_bytes<NOISE>(WARPS);
     OFDM_CUDA(ctx, allow_smem(ctx, k, smem));
     int per_sm = 1;
@@ -259,7 +259,10 @@ int launch_stream_quad_w(ofdm_ctx *ctx, const RxParams &p)
 template <int ARITH, int NOISE>
 int launch_stream_quad(ofdm_ctx *ctx, const RxParams &p)
 {
-    return ctx->stream_warps == 8 ? launch_stream_quad_w<ARITH, NOISE, 8>(ctx, p) : launch_stream_quad_w<ARITH, NOISE, 6>(ctx, p);
+    if (ctx->stream_warps == 8) return launch_stream_quad_w<ARITH, NOISE, 8>(ctx, p);
+    // the default frame shape has its own build: unit w of a quad always in ring slot w ("general_stream" = 1 keeps the general one)
+    if (p.n_sym == 2 && !ctx->general_stream) return launch_stream_quad_w<ARITH, NOISE, 6, true>(ctx, p);
+    return launch_stream_quad_w<ARITH, NOISE, 6>(ctx, p);
 }
 // error radii of the speculating EXACT kernels (ofdm_chain.cuh: kRadius, kChanRadius)
 void set_radius(ofdm_ctx *ctx, RxParams &q)

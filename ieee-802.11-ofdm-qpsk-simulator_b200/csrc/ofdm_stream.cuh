@@ -46,7 +46,7 @@ template <> struct alignas(16) QuadSlot<false> { float2 x[4][kWin]; };
 #define OFDM_QUAD_DEPTH 4               // A/B knobs (tools/ab.sh): ring slots per warp without / with injected draws
 #endif
 #ifndef OFDM_QUAD_DEPTH_DRAWS
-#define OFDM_QUAD_DEPTH_DRAWS 3
+#define OFDM_QUAD_DEPTH_DRAWS 4
 #endif
 template <int NOISE> __host__ __device__ constexpr int quad_depth() { return NOISE == kNoiseInject ? OFDM_QUAD_DEPTH_DRAWS : OFDM_QUAD_DEPTH; }
 
@@ -131,13 +131,20 @@ __device__ __forceinline__ void quad_slot(float2 F, float2 G, float inv2, uint32
     acc_q = __funnelshift_l(__float_as_uint(S.y), acc_q, 1);
 }
 
-template <int ARITH, int NOISE, int WARPS>
+// NSYM2 (the default frame shape, two data symbols): a quad has four units and the ring four slots, so unit w of every quad
+// travels through slot w, one quad ahead of its use -- slot, barrier, window offset and frame pitch are compile-time constants
+// at each of the four places a unit is taken, and a refill is an elected lane adding immediates to the next quad's base
+// address (23 instead of 42 instructions per refill; the refill path was 23 % of the general kernel's stall samples).
+template <int W> struct UnitIndex { static constexpr int value = W; };
+
+template <int ARITH, int NOISE, int WARPS, bool NSYM2 = false>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
 {
     static_assert(ARITH == kArithFast || ARITH == kArithChecked, "the all-exact arithmetic runs in k_stream_rx2 / k_stream_rxn");
     constexpr int LEVEL = ARITH == kArithChecked ? 2 : 1;
     constexpr int DEPTH = quad_depth<NOISE>();
     constexpr bool DRAWS = NOISE == kNoiseInject;
+    static_assert(!NSYM2 || DEPTH == 4, "NSYM2: one ring slot per unit of a quad");
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ unsigned long long s_cnt[WARPS][4];
     __shared__ double s_sum[WARPS][2];
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
     float2 *tile = ws.tile + grp * kGroupPitch;
     Tw<false> tw; tw.load(u);
     const QuadLane ql = make_quad_lane(u);
-    const int n_sym = p.n_sym, len = 160 + 80 * n_sym;
+    const int n_sym = NSYM2 ? 2 : p.n_sym, len = 160 + 80 * n_sym;
     const long n_quads = (p.n_frames + 3) >> 2;
     const long wstride = (long)gridDim.x * WARPS;
     const long q_first = (long)blockIdx.x * WARPS + warp_u;
@@ -204,18 +211,54 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
             }
         }
     };
+    // NSYM2: the quad whose units the next refills fetch (the one after the quad being consumed): base addresses, frames in it
+    const char *nx = reinterpret_cast<const char *>(p.in) + 4 * len8 * q_first;
+    const char *ng = reinterpret_cast<const char *>(p.g) + 4 * len4 * q_first;
+    int n_next = 0;
+    auto refill = [&](auto Wc) {
+        constexpr int W = decltype(Wc)::value;
+        constexpr int n0 = W == 0 ? 32 : (W == 1 ? 96 : (W == 2 ? 176 : 256));                // :837, :838, :1028
+        constexpr long kLen8 = 320 * 8, kLen4 = 320 * 4;
+        if (n_next > 0) {
+            if (tma::elect_one()) {
+                const uint32_t bar = bar0 + 8u * W;
+                const uint32_t dst = slot0 + (uint32_t)W * (uint32_t)sizeof(QS);
+                const uint32_t gd = dst + 4 * kWin * 8;
+                tma::expect_tx_addr(bar, (uint32_t)n_next * (DRAWS ? 768u : 512u));
+                if (n_next == 4) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        tma::bulk_addr(dst + (uint32_t)g * kWin * 8, nx + (n0 * 8 + g * kLen8), 512, bar);
+                        if (DRAWS) tma::bulk_addr(gd + (uint32_t)g * kWin * 4, ng + (n0 * 4 + g * kLen4), 256, bar);
+                    }
+                } else {                                          // the last quad of the batch, when it is not whole
+                    for (int g = 0; g < n_next; ++g) {
+                        tma::bulk_addr(dst + (uint32_t)g * kWin * 8, nx + (n0 * 8 + g * kLen8), 512, bar);
+                        if (DRAWS) tma::bulk_addr(gd + (uint32_t)g * kWin * 4, ng + (n0 * 4 + g * kLen4), 256, bar);
+                    }
+                }
+            }
+        }
+    };
     if (lane == 0) {
         for (int s = 0; s < DEPTH; ++s) tma::mbar_init(&ws.bar[s], 1);
         tma::fence_mbar_init();
     }
     __syncwarp();
+    if constexpr (NSYM2) {
+        const long left = p.n_frames - 4 * q_first;
+        n_next = left <= 0 ? 0 : (left < 4 ? (int)left : 4);      // the warp's first quad
+        refill(UnitIndex<0>{}); refill(UnitIndex<1>{}); refill(UnitIndex<2>{}); refill(UnitIndex<3>{});
+    } else {
 #pragma unroll 1
-    for (int s = 0; s < DEPTH; ++s) issue_next(s);
+        for (int s = 0; s < DEPTH; ++s) issue_next(s);
+    }
 
     int cs = 0;                                                   // ring position of the unit being consumed
     uint32_t cph = 0;
     // pull the lane's eight samples of the current unit (v[m] = x[u + 8m]), add the noise, release the slot
-    auto take = [&](float2 (&v)[8], float2 &n2, float sigma_f, long f, int n0) {
+    auto take = [&](auto Wc, float2 (&v)[8], float2 &n2, float sigma_f, long f, int n0) {
+        constexpr int W = decltype(Wc)::value;                    // NSYM2: the unit's place in the quad = its ring slot
         float z[8];
         if constexpr (NOISE == kNoisePhilox) {                    // Philox noise of the window that starts at sample n0
             const int blk = window_block_base(n0) + u;
@@ -225,8 +268,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
 #pragma unroll
             for (int m = 0; m < 4; ++m) { z[m] = za[m]; z[4 + m] = zb[m]; }
         }
-        tma::wait_addr(bar0 + 8u * (uint32_t)cs, cph);
-        const QS &sl = ws.slot[cs];
+        tma::wait_addr(bar0 + 8u * (uint32_t)(NSYM2 ? W : cs), cph);
+        const QS &sl = ws.slot[NSYM2 ? W : cs];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             float2 smp = sl.x[grp][u + 8 * m];
@@ -236,8 +279,13 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
             v[m] = smp;
         }
         __syncwarp();                                             // every lane has its samples: the slot can be refilled
-        issue_next(cs);
-        if (++cs == DEPTH) { cs = 0; cph ^= 1u; }
+        if constexpr (NSYM2) {
+            refill(Wc);
+            if (W == 3) cph ^= 1u;
+        } else {
+            issue_next(cs);
+            if (++cs == DEPTH) { cs = 0; cph ^= 1u; }
+        }
     };
 
     uint32_t a_i = 0, a_q = 0, a_both = 0, a_ferr = 0, a_frames = 0;     // per lane
@@ -256,6 +304,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
             const int jq = jc + kk;
             if (jq >= my_quads) break;
             const long f0 = 4 * (q_first + (long)jq * wstride);
+            if constexpr (NSYM2) {                                // this quad's refills fetch the warp's next quad
+                const long f0n = f0 + 4 * wstride, left = p.n_frames - f0n;
+                nx = reinterpret_cast<const char *>(p.in) + f0n * (320 * 8);
+                ng = reinterpret_cast<const char *>(p.g) + f0n * (320 * 4);
+                n_next = left <= 0 ? 0 : (left < 4 ? (int)left : 4);
+            }
             const long f = f0 + grp;
             const bool active = f < p.n_frames;                   // only the batch's last quad can have idle groups: they compute along on stale samples
             const float sigma_f = NOISE != kNoiseNone ? __shfl_sync(0xffffffffu, sig_mine, 4 * kk + grp) : 0.f;
@@ -271,8 +325,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
             {
                 float2 b[8];
                 float2 n2 = make_float2(0.f, 0.f);
-                take(G, n2, sigma_f, f, 32);
-                take(b, n2, sigma_f, f, 96);
+                take(UnitIndex<0>{}, G, n2, sigma_f, f, 32);
+                take(UnitIndex<1>{}, b, n2, sigma_f, f, 96);
 #pragma unroll
                 for (int m = 0; m < 8; ++m) G[m] = cadd(G[m], b[m]);
                 // 2 r_H = kRadius (|a|_2 + |b|_2) + 2 chan, and |a|_2 + |b|_2 <= sqrt(2) sqrt(|a|_2^2 + |b|_2^2)
@@ -297,13 +351,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
             uint32_t f_i = 0, f_q = 0, f_both = 0;
             float2 e2v = make_float2(0.f, 0.f);
             // ---- data symbols :1020-1069 against the estimate in registers
-#pragma unroll 1
-            for (int s = 0; s < n_sym; ++s) {
+            auto symbol = [&](auto Wc, int s) {
                 const uint32_t w0 = nw0 ^ ql.flip0, w1 = nw1 ^ ql.flip1, w2 = nw2 ^ ql.flip2;
                 if (s + 1 < n_sym) { wb += 3; nw0 = __ldg(wb); nw1 = __ldg(wb + 1); nw2 = __ldg(wb + 2); }
                 float2 v[8];
                 float2 n2 = make_float2(0.f, 0.f);
-                take(v, n2, sigma_f, f, 176 + 80 * s);
+                take(Wc, v, n2, sigma_f, f, 176 + 80 * s);
                 float rF = 0.f;
                 if (LEVEL >= 2) rF = window_radius(n2, p.radius_scale, chan);
                 fft64_fast(v, tw.t, tile, u);
@@ -323,6 +376,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
                 if (LEVEL >= 2) doubt = doubt || (acc_s & ql.valid_rev) != ql.valid_rev;       // every data bin's decision must be trusted
                 acc_i &= ql.valid_rev; acc_q &= ql.valid_rev;
                 f_i += __popc(acc_i); f_q += __popc(acc_q); f_both += __popc(acc_i & acc_q);
+            };
+            if constexpr (NSYM2) { symbol(UnitIndex<2>{}, 0); symbol(UnitIndex<3>{}, 1); }
+            else {
+#pragma unroll 1
+                for (int s = 0; s < n_sym; ++s) symbol(UnitIndex<0>{}, s);
             }
             float f_e2 = e2v.x + e2v.y;
             if (!active) { f_i = 0; f_q = 0; f_both = 0; f_e2 = 0.f; doubt = false; }
