@@ -105,8 +105,8 @@ int ofdm_ctx_sync(ofdm_ctx *ctx);
  *                            k_stream_rxn / k_mc_philox) instead of one frame per 8-lane group (k_stream_quad / k_mc_quad,
  *                            default 0; same totals in EXACT mode, DESIGN.md sections 4.5, 4.6)
  *   "stream_warps"      = 8  k_stream_quad in blocks of 8 warps (128 registers) instead of 6 (168 registers, default)
- *   "general_stream"    = 1  with "stream_layout" = 1: two-symbol frames also take the multi-pass streaming kernel that serves
- *                            every other frame shape
+ *   "general_stream"    = 1  two-symbol frames take the build that serves every other frame shape too (k_stream_quad without its
+ *                            compile-time ring slots; with "stream_layout" = 1: the multi-pass k_stream_rxn)
  *   "evm_guard"         = N  bins whose channel estimate is smaller than N error radii are replayed exactly (default 820): the
  *                            EVM sums' distance from the all-exact kernel's against the number of replays
  *   "power_margin"      = N  the exact frame power speculates each term of the serial float sum as x^2 + y^2 and takes the
