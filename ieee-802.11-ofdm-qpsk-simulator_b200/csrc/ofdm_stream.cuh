@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_stream_quad(RxParams p)
     // pull the lane's eight samples of the current unit (v[m] = x[u + 8m]), add the noise, release the slot
     auto take = [&](auto Wc, float2 (&v)[8], float2 &n2, float sigma_f, long f, int n0) {
         constexpr int W = decltype(Wc)::value;                    // NSYM2: the unit's place in the quad = its ring slot
-        float z[8];
+        [[maybe_unused]] float z[8];
         if constexpr (NOISE == kNoisePhilox) {                    // Philox noise of the window that starts at sample n0
             const int blk = window_block_base(n0) + u;
             float za[4], zb[4];
