@@ -119,3 +119,14 @@ def test_shard_range_and_counter_packing(pkg):
     i, d = sw.counters_to_arrays([c, c])
     back = sw.arrays_to_counters(i, d)
     assert back[1].as_dict() == c.as_dict()
+
+
+def test_every_documented_option_is_handled_and_vice_versa():
+    """include/ofdm_b200.h documents the knobs of ofdm_ctx_set_option; csrc/ofdm_b200.cu handles them: the two lists must agree"""
+    import re
+    header = open(os.path.join(ROOT, "include", "ofdm_b200.h")).read()
+    source = open(os.path.join(ROOT, "ieee-802.11-ofdm-qpsk-simulator_b200", "csrc", "ofdm_b200.cu")).read()
+    block = header[header.index("int ofdm_ctx_set_option") - 4000:header.index("int ofdm_ctx_set_option")]
+    documented = set(re.findall(r'\*\s+"([a-z_]+)"\s+=', block))
+    handled = set(re.findall(r'!strcmp\(name, "([a-z_]+)"\)', source))
+    assert handled and documented == handled, (sorted(documented - handled), sorted(handled - documented))
